@@ -1,0 +1,124 @@
+/*
+ * vpt_b200.h -- C ABI of libvpt_b200.so, the B200-native replacement for the reference render pass.
+ *
+ * Drop-in boundary.  The reference application issues one progressive pass as
+ *
+ *     void* params[] = { &cam, &l_list, &d_volume_ptr, &d_geo_ptr, &d_geo_list_ptr,
+ *                        &bvh_builder.bvh.BVHNodes, &bvh_builder.root, atmos_params, &kernel_params };
+ *     cuLaunchKernel(cuRaycastKernel, grid.x, grid.y, 1, 16, 16, 1, 0, NULL, params, NULL);   // main.cpp:1826-1827
+ *
+ * and the replacement is that one line:
+ *
+ *     vpt_render_pass(ctx, params, NULL);
+ *
+ * with the very same `params` array (layouts in vpt_abi.h).  All memory named by the parameters stays
+ * owned by the caller, exactly as with the reference kernel; the context only owns its ray queue,
+ * sample planes and the flattened scene tables it derives from GPU_VDB[] + the OCTNode tree.
+ *
+ * Every function returns 0 on success or a negative VPT_ERR_* code; vpt_last_error() gives the text.
+ * There is no CPU fallback: without a CUDA device every entry point fails with VPT_ERR_CUDA.
+ */
+#ifndef VPT_B200_H_
+#define VPT_B200_H_
+
+#include "vpt_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPT_OK                 0
+#define VPT_ERR_INVALID       -1   /* bad argument */
+#define VPT_ERR_CUDA          -2   /* CUDA runtime / driver failure (text in vpt_last_error) */
+#define VPT_ERR_UNSUPPORTED   -3   /* parameter combination this build does not implement */
+#define VPT_ERR_IO            -4   /* file could not be read / decoded */
+
+typedef struct vpt_context vpt_context;
+
+/* ---- lifecycle ----------------------------------------------------------------------------------- */
+int  vpt_create(vpt_context** out);                    /* binds to the calling thread's current CUDA device */
+void vpt_destroy(vpt_context* ctx);
+const char* vpt_last_error(const vpt_context* ctx);    /* ctx may be NULL: error of the last failed vpt_create / helper */
+const char* vpt_version(void);
+/* sizeof() of the boundary structs: camera, light_list, GPU_VDB, sphere, geometry_list, BVHNode, OCTNode,
+ * AtmosphereParameters, Kernel_params, point_light, VDB_INFO, AABB.  Returns how many entries exist. No CUDA call. */
+int  vpt_abi_sizes(size_t* out, int n);
+
+/* Tunables: "passes_per_chunk" (1..64, passes fused per generate/trace/resolve round, default 8),
+ * "service_threshold" (8|16|20|24|32 lanes that must be inside a walk to keep the step loop running),
+ * "ctas_per_sm" (0 = occupancy maximum). */
+int  vpt_set_option(vpt_context* ctx, const char* key, int value);
+
+/* Multi-GPU partition of the frame: rank r of n renders the interleaved row stripes r, r+n, ... of
+ * `stripe_rows` rows.  With n_ranks > 1 every buffer inside Kernel_params (accum, depth, cost, raw,
+ * display) holds vpt_local_pixels() pixels in rank-local order; the blue-noise buffer stays a full
+ * 256x256 replica.  Default: one rank, identity layout (bit-compatible with the reference buffers). */
+int  vpt_set_partition(vpt_context* ctx, int rank, int n_ranks, int stripe_rows);
+long long vpt_local_pixels(const vpt_context* ctx, unsigned width, unsigned height);
+/* After an all-gather of rank-local buffers ([rank][local pixel], elem_bytes per pixel, multiple of 4)
+ * scatter them back into a full row-major frame. */
+int  vpt_unpermute(vpt_context* ctx, const void* d_gathered, void* d_full, unsigned width, unsigned height,
+                   int elem_bytes, void* stream);
+
+/* ---- the hot path --------------------------------------------------------------------------------
+ * vpt_render_pass   replaces ONE launch of the reference `volume_rt_kernel` (render_kernel.cu:2216):
+ *                   same inputs, same buffer updates (accum/depth/cost running means, display, raw,
+ *                   blue-noise advance).  The caller keeps doing `++kernel_params.iteration`.
+ * vpt_render_passes is n consecutive such launches with iteration, iteration+1, ... fused into as few
+ *                   kernel rounds as the chunk size allows; the buffers afterwards equal the state after
+ *                   n reference launches (display/raw are written once, from the final accumulator).
+ * `params` is the cuLaunchKernel argument array (VPT_ARG_* in vpt_abi.h). `stream` is a cudaStream_t.
+ * Work is enqueued asynchronously; synchronise the stream (or the device) as the reference loop does. */
+int  vpt_render_pass(vpt_context* ctx, void* const params[VPT_NUM_ARGS], void* stream);
+int  vpt_render_passes(vpt_context* ctx, void* const params[VPT_NUM_ARGS], unsigned n_passes, void* stream);
+
+/* The flattened scene tables are cached per (volumes pointer, octree root pointer); call this after the
+ * application rebuilt either in place. */
+int  vpt_invalidate_scene(vpt_context* ctx);
+
+/* Counters of the last vpt_render_pass(es) call: kernels launched, and (after the stream has been
+ * synchronised by the caller) rays pushed into the hit queue by the final chunk. */
+int  vpt_get_stats(vpt_context* ctx, unsigned long long* kernel_launches_total, unsigned* last_queue_count);
+
+/* ---- host-side scene helpers (what the reference does in main.cpp / gpu_vdb.cpp / bvh_builder.cpp) -- */
+
+/* Dense grid -> 3-D texture, as GPU_VDB::loadVDB builds them (gpu_vdb.cpp:215-248: cudaArray, normalised
+ * coordinates, linear filter, clamp).  channels = 1 (float) or 4 (float4).  Returns the texture object and
+ * an opaque array handle for vpt_texture_destroy. */
+int  vpt_texture_create_3d(const float* host_data, int channels, int dim_x, int dim_y, int dim_z,
+                           vpt_tex_t* tex_out, void** array_out);
+/* Equirectangular environment map float4 (main.cpp:945-978: wrap / clamp, linear, normalised). */
+int  vpt_texture_create_env(const float* host_rgba, unsigned width, unsigned height, vpt_tex_t* tex_out, void** array_out);
+int  vpt_texture_destroy(vpt_tex_t tex, void* array);
+
+/* Minimal OpenVDB (file format 224) reader: densify grid `grid_name` over its active-voxel bounding box
+ * (gpu_vdb.cpp:133-212).  On success *values_out is malloc'd (x fastest, `channels` floats per voxel; free
+ * with vpt_free) and info[] receives: dim[3], bbox_min[3], bbox_max[3], channels, leaf_count,
+ * active_voxel_count (lo, hi 32 bits)  -> 13 ints; xform16 receives the reference's mat4 memory image
+ * (gpu_vdb.cpp:81-92, convert_to_mat4); stats[] = { max_value, min_density per Q10, voxel_size, background }.
+ * Returns 1 if the file has no such grid. */
+int  vpt_vdb_load(const char* path, const char* grid_name, float** values_out, int info[13], float xform16[16], float stats[4]);
+int  vpt_hdr_load(const char* path, float** rgba_out, unsigned* width, unsigned* height);   /* hdr_loader.h:249-278 */
+int  vpt_bmp_load_rbg(const char* path, float** xyz_out, int* width, int* height);          /* fileIO.cpp:460-495 (Q16) */
+int  vpt_exr_load_rgb(const char* path, float** rgb_out, int* width, int* height);          /* fileIO.cpp:356-390 */
+void vpt_free(void* p);
+
+/* Depth-3 octree over instance bounds in the reference's own node layout (bvh_builder.cpp:61-96 +
+ * bvh_kernels.cu:204-246), built in parallel (one thread per node, no device heap, no 600-volume
+ * overflow: n > VPT_OCT_MAX_VOLUMES is rejected).  h_volumes: host array of n GPU_VDB.
+ * *d_root_out: device pointer to node 0 of a contiguous 585-node array (free with vpt_octree_destroy). */
+int  vpt_octree_build(const vpt_gpu_vdb* h_volumes, int n, vpt_devptr_t* d_root_out);
+int  vpt_octree_destroy(vpt_devptr_t d_root);
+/* AABB of one instance (GPU_VDB::Bounds, gpu_vdb.h:131-146): out6 = pmin, pmax. */
+void vpt_volume_bounds(const vpt_gpu_vdb* h_volume, float out6[6]);
+
+/* Thin-lens camera set-up (camera::update_camera, camera.h:110-129). */
+void vpt_camera_look_at(vpt_camera* cam, const float lookfrom[3], const float lookat[3], const float vup[3],
+                        float vfov_deg, float aspect, float aperture);
+/* Kernel_params defaults of main.cpp:1350-1376 with the frame-loop overrides (:1533-1544). */
+void vpt_kernel_params_defaults(vpt_kernel_params* kp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPT_B200_H_ */

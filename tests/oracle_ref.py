@@ -1,0 +1,85 @@
+"""Test-side wrapper of the ORACLE: the reference's own `volume_rt_kernel`, octree builder and
+blue-noise update, compiled from /root/reference by oracle/Makefile into oracle/_ref/.
+
+Only tests/, __graft_entry__.smoke() and bench.py's reference arm may import this module.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(_REPO, "oracle", "_ref")
+LIB = os.path.join(REF_DIR, "libvpt_ref.so")
+
+
+def available():
+    return all(os.path.exists(os.path.join(REF_DIR, f)) for f in
+               ("libvpt_ref.so", "render_kernel_ref.cubin", "render_kernel_ref_nobn.cubin", "bn_advance_ref.cubin"))
+
+
+class RefOracle:
+    """Drives the reference kernel with a byte-identical parameter block (LaunchParams.array)."""
+    UNMODIFIED, NOBN = 0, 1
+
+    def __init__(self):
+        if not available():
+            raise RuntimeError("oracle/_ref is not built (run `make -C oracle ref` where /root/reference exists)")
+        self.lib = C.CDLL(LIB)
+        L = self.lib
+        L.vptref_load_kernel.argtypes = [C.c_char_p, C.c_int]; L.vptref_load_kernel.restype = C.c_int
+        L.vptref_load_bn_kernel.argtypes = [C.c_char_p]; L.vptref_load_bn_kernel.restype = C.c_int
+        L.vptref_launch.argtypes = [C.POINTER(C.c_void_p), C.c_uint, C.c_uint, C.c_int, C.c_int]; L.vptref_launch.restype = C.c_int
+        L.vptref_bn_advance.argtypes = [C.c_void_p, C.c_int]; L.vptref_bn_advance.restype = C.c_int
+        L.vptref_build_octree.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]; L.vptref_build_octree.restype = C.c_int
+        L.vptref_build_bvh.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_float)]
+        L.vptref_build_bvh.restype = C.c_int
+        L.vptref_sizes.argtypes = [C.POINTER(C.c_size_t), C.c_int]; L.vptref_sizes.restype = C.c_int
+        L.vptref_update_camera.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float]
+        L.vptref_bounds.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.vptref_instance_xform.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float)]
+        self._loaded = False
+
+    def load_kernels(self):
+        if self._loaded:
+            return
+        for which, name in ((0, "render_kernel_ref.cubin"), (1, "render_kernel_ref_nobn.cubin")):
+            rc = self.lib.vptref_load_kernel(os.path.join(REF_DIR, name).encode(), which)
+            if rc: raise RuntimeError(f"vptref_load_kernel({name}) -> {rc}")
+        rc = self.lib.vptref_load_bn_kernel(os.path.join(REF_DIR, "bn_advance_ref.cubin").encode())
+        if rc: raise RuntimeError(f"vptref_load_bn_kernel -> {rc}")
+        self._loaded = True
+
+    def sizes(self):
+        out = (C.c_size_t * 12)(); n = self.lib.vptref_sizes(out, 12)
+        return list(out)[:n]
+
+    def build_octree(self, h_volumes, n):
+        """Reference octree (device heap).  Returns the device root pointer."""
+        root = C.c_void_p(0)
+        rc = self.lib.vptref_build_octree(C.cast(h_volumes, C.c_void_p), n, C.byref(root))
+        if rc: raise RuntimeError(f"vptref_build_octree -> {rc}")
+        return root.value
+
+    def launch(self, params_array, width, height, which=NOBN, sync=True):
+        """One progressive pass exactly as main.cpp:1823-1829 issues it (caller bumps kp.iteration)."""
+        self.load_kernels()
+        rc = self.lib.vptref_launch(params_array, width, height, which, 1 if sync else 0)
+        if rc: raise RuntimeError(f"vptref_launch -> {rc}")
+
+    def bn_advance(self, kp, sync=True):
+        self.load_kernels()
+        rc = self.lib.vptref_bn_advance(C.cast(C.byref(kp), C.c_void_p), 1 if sync else 0)
+        if rc: raise RuntimeError(f"vptref_bn_advance -> {rc}")
+
+    def render(self, renderer, n_passes, race_free=True):
+        """Run n reference passes on `renderer`'s parameter block and buffers (race-free protocol: the
+        'nobn' build + the reference's own blue-noise statements as a separate launch)."""
+        for _ in range(n_passes):
+            if race_free:
+                self.launch(renderer.params.array, renderer.width, renderer.height, self.NOBN)
+                self.bn_advance(renderer.kp)
+            else:
+                self.launch(renderer.params.array, renderer.width, renderer.height, self.UNMODIFIED)
+            renderer.kp.iteration += 1
+        torch.cuda.synchronize()

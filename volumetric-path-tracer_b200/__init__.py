@@ -1,0 +1,15 @@
+"""volumetric-path-tracer_b200: B200-native (sm_100a) replacement for the render pass of
+sergeneren/Volumetric-Path-Tracer, behind the reference's own launch-parameter ABI.
+
+The directory name carries a hyphen (it mirrors the reference's repository name); import it through the
+top-level shim `vpt_b200` (repo root), which loads this package under that name.
+"""
+from ._native import (lib, VptError, camera, light_list, point_light, GPU_VDB, VDB_INFO, AABB, OCTNode, BVHNode, sphere,
+                      geometry_list, AtmosphereParameters, Kernel_params, f3, i3, u2, LIB_PATH)
+from .scene import Scene, Volume, default_kernel_params, find_asset
+from .renderer import Renderer, DistributedRenderer, FrameBuffers, LaunchParams, stripe_rows_of_rank
+
+__all__ = ["lib", "VptError", "camera", "light_list", "point_light", "GPU_VDB", "VDB_INFO", "AABB", "OCTNode", "BVHNode",
+           "sphere", "geometry_list", "AtmosphereParameters", "Kernel_params", "f3", "i3", "u2", "Scene", "Volume",
+           "default_kernel_params", "find_asset", "Renderer", "DistributedRenderer", "FrameBuffers", "LaunchParams",
+           "stripe_rows_of_rank", "LIB_PATH"]

@@ -1,0 +1,17 @@
+#!/bin/bash
+# Builds libvpt_b200.so (the product) in-tree for sm_100a.  nvcc cross-compiles without a GPU.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/../lib"
+mkdir -p "$OUT" "$HERE/_obj"
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+NVCC="${NVCC:-nvcc}"
+# kernels: the reference's numeric flags (--use_fast_math) so per-seed parity is reachable
+$NVCC $ARCH -O3 --use_fast_math -lineinfo -std=c++17 -Xcompiler -fPIC -c "$HERE/device/vpt_kernels.cu" -o "$HERE/_obj/vpt_kernels.o"
+# octree build: plain IEEE flags, as the reference's bvh object
+$NVCC $ARCH -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-ffp-contract=off -c "$HERE/device/vpt_octree.cu" -o "$HERE/_obj/vpt_octree.o"
+$NVCC $ARCH -O2 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off -x cu -c "$HERE/host/vpt_context.cpp" -o "$HERE/_obj/vpt_context.o"
+g++ -O2 -std=c++17 -fPIC -c "$HERE/host/vdb_reader.cpp" -o "$HERE/_obj/vdb_reader.o"
+g++ -O2 -std=c++17 -fPIC -c "$HERE/host/image_io.cpp" -o "$HERE/_obj/image_io.o"
+$NVCC $ARCH -shared -o "$OUT/libvpt_b200.so" "$HERE"/_obj/*.o -lz
+echo "built $OUT/libvpt_b200.so"

@@ -1,0 +1,46 @@
+// vpt_kernels.h -- launch interface between the host context (csrc/host) and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../../include/vpt_abi.h"
+#include "vpt_scene.cuh"
+
+namespace vpt {
+
+constexpr int kTraceThreads = 256;
+
+// Which pixels this rank renders: rows are dealt to ranks in interleaved stripes of `stripe_h` rows
+// (rank r owns stripes r, r+R, r+2R, ...).  One rank: identity mapping, local == global indices.
+struct FrameGeom {
+    int width, height;      // full frame
+    int local_rows;         // rows stored locally (padded so every rank holds the same count)
+    int n_local;            // local_rows * width
+    int stripe_h, n_ranks, rank;
+};
+
+// Everything a per-frame kernel needs, passed by value (about 600 B of kernel parameter space).
+struct FrameArgs {
+    vpt_camera        cam;
+    vpt_light_list    lights;
+    vpt_kernel_params kp;          // buffers inside are indexed by LOCAL pixel
+    const vpt_sphere* sphere;
+    const SceneTables* scene;
+    FrameGeom         geom;
+    // ray queue (hits): 2 x float4 per record, plus its two counters
+    float4*   queue;
+    unsigned* queue_count;
+    unsigned* queue_head;
+    // sample planes, [pass][local pixel]
+    float4 *planeA, *planeB, *planeC, *planeD;   // planeD (env_pos) only for environment_type == 0, else null
+};
+
+cudaError_t launch_prepare_scene(const vpt_gpu_vdb* vols, const vpt_octnode* root, SceneTables* out, OctInternal* internal,
+                                 uint2* leaf_list, int* leaf_indices, VolumeRec* vrec, int max_volumes, cudaStream_t s);
+cudaError_t launch_generate(const FrameArgs& fa, int n_passes, cudaStream_t s);
+cudaError_t launch_trace(const FrameArgs& fa, int n_ctas, int service_threshold, cudaStream_t s);
+int         trace_max_ctas_per_sm(int service_threshold);
+cudaError_t launch_resolve(const FrameArgs& fa, int n_passes, int sampled, int write_display, cudaStream_t s);
+cudaError_t launch_bn_advance(void* bn, int n, cudaStream_t s);
+cudaError_t launch_unpermute(const void* gathered, void* full, const FrameGeom& g, int elem_bytes, cudaStream_t s);
+
+} // namespace vpt

@@ -1,0 +1,95 @@
+// vpt_math.cuh -- small float3 toolkit + counter-based Philox used by every kernel of the path.
+//
+// The render path is a chaotic estimator: one flipped accept/reject comparison changes a pixel's
+// whole remaining path.  Per-seed parity with the reference kernel therefore needs the same IEEE
+// operations in the same order wherever a value feeds a decision.  The expressions below are written
+// in the operand order nvcc's contraction turns into the same mul/fma chains as the reference build
+// (checked against its PTX: sum-of-products -> mul(second) , fma(first) , fma(third) ...), and the
+// translation unit is compiled with the reference's own numeric flags (--use_fast_math).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vpt {
+
+#define VPT_DEV __device__ __forceinline__
+
+#define VPT_EPS      0.001f               // EPS, render_kernel.cu:83
+#define VPT_M_INF    3.402823466e+38F     // M_INF, common/helper_math.h:41
+#define VPT_PI_F     3.14159265358979323846f
+#define VPT_PI_4_F   0.785398163397448309616f   // M_PI_4 (quirk Q1: HG is scaled by pi/4)
+#define VPT_BLACK_EPS 1.192092896e-07F    // isBlack threshold, helper_math.h:1473
+
+VPT_DEV float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+VPT_DEV float3 f3(float s) { return make_float3(s, s, s); }
+VPT_DEV float3 operator+(float3 a, float3 b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
+VPT_DEV float3 operator-(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+VPT_DEV float3 operator*(float3 a, float3 b) { return make_float3(a.x * b.x, a.y * b.y, a.z * b.z); }
+VPT_DEV float3 operator*(float3 a, float s) { return make_float3(a.x * s, a.y * s, a.z * s); }
+VPT_DEV float3 operator*(float s, float3 a) { return make_float3(s * a.x, s * a.y, s * a.z); }
+VPT_DEV float3 operator/(float3 a, float3 b) { return make_float3(a.x / b.x, a.y / b.y, a.z / b.z); }
+VPT_DEV float3 operator/(float3 a, float s) { return make_float3(a.x / s, a.y / s, a.z / s); }
+VPT_DEV void operator+=(float3& a, float3 b) { a.x += b.x; a.y += b.y; a.z += b.z; }
+VPT_DEV void operator*=(float3& a, float3 b) { a.x *= b.x; a.y *= b.y; a.z *= b.z; }
+VPT_DEV void operator*=(float3& a, float s) { a.x *= s; a.y *= s; a.z *= s; }
+VPT_DEV float  dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+VPT_DEV float  length(float3 v) { return sqrtf(dot(v, v)); }
+VPT_DEV float3 normalize(float3 v) { float inv = rsqrtf(dot(v, v)); return v * inv; }
+VPT_DEV float3 cross(float3 a, float3 b) { return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+VPT_DEV float3 lerp3(float3 a, float3 b, float t) { return a + t * (b - a); }
+VPT_DEV float3 reflect3(float3 i, float3 n) { return i - 2.0f * n * dot(n, i); }
+VPT_DEV float  clampf(float f, float a, float b) { return fmaxf(a, fminf(f, b)); }
+VPT_DEV float3 fmax3(float3 a, float3 b) { return make_float3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+VPT_DEV bool   is_black(float3 v) { return length(v) < VPT_BLACK_EPS; }
+VPT_DEV bool   any_nan(float3 v) { return isnan(v.x) || isnan(v.y) || isnan(v.z); }
+VPT_DEV bool   any_inf(float3 v) { return isinf(v.x) || isinf(v.y) || isinf(v.z); }
+
+// ---- Philox4x32-10, addressed by (key, block) instead of carrying the 64-byte cuRAND state ------
+// Reference stream (curand_kernel.h:1022-1037, curand_philox4x32_x.h:93-197):
+// curand_init(seed = pixel idx, subsequence 0, offset = iteration*4096) => key = (idx, 0),
+// counter = ((iteration*4096 mod 2^32) / 4, 0, 0, 0); draw k is lane (k & 3) of block (k >> 2).
+struct PhiloxBlock { uint32_t x, y, z, w; };
+
+VPT_DEV PhiloxBlock philox4x32_10(uint32_t c0, uint32_t c1, uint32_t key0) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    uint32_t x0 = c0, x1 = c1, x2 = 0u, x3 = 0u, k0 = key0, k1 = 0u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, x0), lo0 = M0 * x0;
+        const uint32_t hi1 = __umulhi(M1, x2), lo1 = M1 * x2;
+        const uint32_t n0 = hi1 ^ x1 ^ k0, n1 = lo1, n2 = hi0 ^ x3 ^ k1, n3 = lo0;
+        x0 = n0; x1 = n1; x2 = n2; x3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    PhiloxBlock b; b.x = x0; b.y = x1; b.z = x2; b.w = x3; return b;
+}
+
+// curand_uniform: x * 2^-32 + 2^-33, in (0, 1]  (curand_uniform.h:69-72)
+VPT_DEV float u32_to_unit(uint32_t x) { return x * 2.3283064e-10f + (2.3283064e-10f / 2.0f); }
+
+struct Rng {
+    uint32_t key;      // global pixel index
+    uint32_t base;     // counter word 0 at draw 0: (iteration*4096 mod 2^32) >> 2
+    uint32_t k;        // draws consumed so far
+    uint32_t cached;   // block index held in `blk` (0xffffffff = none)
+    PhiloxBlock blk;
+    VPT_DEV void init(uint32_t key_, uint32_t iteration, uint32_t k0) {
+        key = key_; base = (iteration * 4096u) >> 2; k = k0; cached = 0xffffffffu;
+    }
+    VPT_DEV float next() {
+        const uint32_t b = k >> 2;
+        if (b != cached) {
+            // 64-bit counter increment as curand's Philox_State_Incr: carry from word 0 into word 1
+            const uint32_t c0 = base + b;
+            const uint32_t c1 = (c0 < base) ? 1u : 0u;
+            blk = philox4x32_10(c0, c1, key);
+            cached = b;
+        }
+        const uint32_t lane = k & 3u;
+        const uint32_t v = lane == 0 ? blk.x : lane == 1 ? blk.y : lane == 2 ? blk.z : blk.w;
+        ++k;
+        return u32_to_unit(v);
+    }
+};
+
+} // namespace vpt

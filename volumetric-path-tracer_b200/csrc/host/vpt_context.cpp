@@ -1,0 +1,468 @@
+// vpt_context.cpp -- C-ABI implementation (include/vpt_b200.h): context, render-pass scheduling,
+// scene-table cache, and the host-side scene helpers.
+//
+// Scheduling of one vpt_render_passes(n) call on the caller's stream (no host synchronisation):
+//   [once per (volumes, octree) pair]  k_prepare_scene
+//   for each chunk of <= passes_per_chunk sampled passes:
+//        memset(queue counters) -> k_generate -> k_trace (persistent) -> k_resolve
+//   k_bn_advance(n)
+// which leaves every buffer named by Kernel_params in the state n reference launches would.
+#include "../../../include/vpt_b200.h"
+#include "../device/vpt_kernels.h"
+#include "vdb_reader.h"
+#include "image_io.h"
+
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iterator>
+#include <string>
+#include <vector>
+
+namespace vpt {
+cudaError_t octree_build_device(vpt_octnode* d_nodes, const vpt_gpu_vdb* d_vols, int n, cudaStream_t s);
+void instance_bounds_host(const vpt_gpu_vdb& g, float out6[6]);
+}
+
+static thread_local std::string g_last_error;
+
+struct vpt_context {
+    int device = 0;
+    int num_sms = 0;
+    std::string err;
+    // options
+    int passes_per_chunk = 8;
+    int service_threshold = 20;
+    int ctas_per_sm = 0;
+    // partition
+    int rank = 0, n_ranks = 1, stripe_rows = 16;
+    // scene cache
+    vpt_devptr_t cached_volumes = 0, cached_root = 0;
+    vpt::SceneTables* d_scene = nullptr;
+    vpt::OctInternal* d_internal = nullptr;
+    uint2* d_leaf_list = nullptr;
+    int* d_leaf_indices = nullptr;
+    vpt::VolumeRec* d_vrec = nullptr;
+    // frame buffers
+    size_t cap_samples = 0;           // n_local * chunk
+    bool   cap_planeD = false;
+    float4 *d_queue = nullptr, *d_planeA = nullptr, *d_planeB = nullptr, *d_planeC = nullptr, *d_planeD = nullptr;
+    unsigned* d_counters = nullptr;   // [0] queue_count, [1] queue_head
+    // stats
+    unsigned long long launches = 0;
+};
+
+static int fail(vpt_context* ctx, int code, const std::string& msg) {
+    g_last_error = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+#define VPT_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(ctx, VPT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+static vpt::FrameGeom make_geom(const vpt_context* c, unsigned w, unsigned h) {
+    vpt::FrameGeom g;
+    g.width = (int)w; g.height = (int)h; g.n_ranks = c->n_ranks; g.rank = c->rank;
+    if (c->n_ranks == 1) { g.stripe_h = (int)h > 0 ? (int)h : 1; g.local_rows = (int)h; }
+    else {
+        g.stripe_h = c->stripe_rows;
+        const int stripes = ((int)h + g.stripe_h - 1) / g.stripe_h;
+        const int per_rank = (stripes + c->n_ranks - 1) / c->n_ranks;
+        g.local_rows = per_rank * g.stripe_h;
+    }
+    g.n_local = g.local_rows * g.width;
+    return g;
+}
+
+extern "C" {
+
+const char* vpt_version(void) { return "vpt-b200 0.1 (sm_100a wavefront build)"; }
+
+// sizeof of every boundary struct, in VPT_ARG order then the auxiliary ones (no CUDA call: usable on a CPU-only host)
+int vpt_abi_sizes(size_t* out, int n) {
+    const size_t s[] = { sizeof(vpt_camera), sizeof(vpt_light_list), sizeof(vpt_gpu_vdb), sizeof(vpt_sphere), sizeof(vpt_geometry_list),
+                         sizeof(vpt_bvhnode), sizeof(vpt_octnode), sizeof(vpt_atmosphere), sizeof(vpt_kernel_params),
+                         sizeof(vpt_point_light), sizeof(vpt_vdb_info), sizeof(vpt_aabb) };
+    const int m = (int)(sizeof(s) / sizeof(s[0]));
+    for (int i = 0; i < n && i < m; ++i) out[i] = s[i];
+    return m;
+}
+
+const char* vpt_last_error(const vpt_context* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int vpt_create(vpt_context** out) {
+    if (!out) return fail(nullptr, VPT_ERR_INVALID, "vpt_create: null output pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, VPT_ERR_CUDA, std::string("vpt_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
+    vpt_context* c = new vpt_context();
+    VPT_CUDA(c, cudaGetDevice(&c->device));
+    cudaDeviceProp prop;
+    VPT_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major < 10) { std::string m = "vpt_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ", kernels are built for sm_100a only"; delete c; return fail(nullptr, VPT_ERR_UNSUPPORTED, m); }
+    c->num_sms = prop.multiProcessorCount;
+    VPT_CUDA(c, cudaMalloc(&c->d_scene, sizeof(vpt::SceneTables)));
+    VPT_CUDA(c, cudaMalloc(&c->d_internal, sizeof(vpt::OctInternal) * vpt::kOctInternalNodes));
+    VPT_CUDA(c, cudaMalloc(&c->d_leaf_list, sizeof(uint2) * vpt::kOctLeaves));
+    VPT_CUDA(c, cudaMalloc(&c->d_leaf_indices, sizeof(int) * vpt::kOctLeaves * VPT_OCT_MAX_VOLUMES));
+    VPT_CUDA(c, cudaMalloc(&c->d_vrec, sizeof(vpt::VolumeRec) * VPT_OCT_MAX_VOLUMES));
+    VPT_CUDA(c, cudaMalloc(&c->d_counters, sizeof(unsigned) * 4));
+    *out = c;
+    return VPT_OK;
+}
+
+void vpt_destroy(vpt_context* c) {
+    if (!c) return;
+    cudaFree(c->d_scene); cudaFree(c->d_internal); cudaFree(c->d_leaf_list); cudaFree(c->d_leaf_indices); cudaFree(c->d_vrec);
+    cudaFree(c->d_counters); cudaFree(c->d_queue); cudaFree(c->d_planeA); cudaFree(c->d_planeB); cudaFree(c->d_planeC); cudaFree(c->d_planeD);
+    delete c;
+}
+
+int vpt_set_option(vpt_context* c, const char* key, int value) {
+    if (!c || !key) return fail(c, VPT_ERR_INVALID, "vpt_set_option: null argument");
+    const std::string k(key);
+    if (k == "passes_per_chunk") { if (value < 1 || value > 64) return fail(c, VPT_ERR_INVALID, "passes_per_chunk must be 1..64"); c->passes_per_chunk = value; }
+    else if (k == "service_threshold") { if (value != 8 && value != 16 && value != 20 && value != 24 && value != 32) return fail(c, VPT_ERR_INVALID, "service_threshold must be one of 8,16,20,24,32"); c->service_threshold = value; }
+    else if (k == "ctas_per_sm") { if (value < 0 || value > 8) return fail(c, VPT_ERR_INVALID, "ctas_per_sm must be 0..8"); c->ctas_per_sm = value; }
+    else return fail(c, VPT_ERR_INVALID, "unknown option " + k);
+    return VPT_OK;
+}
+
+int vpt_set_partition(vpt_context* c, int rank, int n_ranks, int stripe_rows) {
+    if (!c || n_ranks < 1 || rank < 0 || rank >= n_ranks || stripe_rows < 1) return fail(c, VPT_ERR_INVALID, "vpt_set_partition: bad arguments");
+    c->rank = rank; c->n_ranks = n_ranks; c->stripe_rows = stripe_rows;
+    return VPT_OK;
+}
+
+long long vpt_local_pixels(const vpt_context* c, unsigned width, unsigned height) {
+    if (!c) return -1;
+    return make_geom(c, width, height).n_local;
+}
+
+int vpt_unpermute(vpt_context* c, const void* d_gathered, void* d_full, unsigned width, unsigned height, int elem_bytes, void* stream) {
+    if (!c || !d_gathered || !d_full || elem_bytes <= 0 || (elem_bytes & 3)) return fail(c, VPT_ERR_INVALID, "vpt_unpermute: bad arguments");
+    const vpt::FrameGeom g = make_geom(c, width, height);
+    VPT_CUDA(c, vpt::launch_unpermute(d_gathered, d_full, g, elem_bytes, (cudaStream_t)stream));
+    c->launches++;
+    return VPT_OK;
+}
+
+int vpt_invalidate_scene(vpt_context* c) {
+    if (!c) return VPT_ERR_INVALID;
+    c->cached_volumes = 0; c->cached_root = 0;
+    return VPT_OK;
+}
+
+int vpt_get_stats(vpt_context* c, unsigned long long* launches, unsigned* last_queue_count) {
+    if (!c) return VPT_ERR_INVALID;
+    if (launches) *launches = c->launches;
+    if (last_queue_count) VPT_CUDA(c, cudaMemcpy(last_queue_count, c->d_counters, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    return VPT_OK;
+}
+
+static int ensure_frame_buffers(vpt_context* c, size_t n_samples, bool need_planeD) {
+    if (n_samples > c->cap_samples) {
+        cudaFree(c->d_queue); cudaFree(c->d_planeA); cudaFree(c->d_planeB); cudaFree(c->d_planeC); cudaFree(c->d_planeD);
+        c->d_queue = c->d_planeA = c->d_planeB = c->d_planeC = c->d_planeD = nullptr; c->cap_samples = 0; c->cap_planeD = false;
+        VPT_CUDA(c, cudaMalloc(&c->d_queue, n_samples * 2 * sizeof(float4)));
+        VPT_CUDA(c, cudaMalloc(&c->d_planeA, n_samples * sizeof(float4)));
+        VPT_CUDA(c, cudaMalloc(&c->d_planeB, n_samples * sizeof(float4)));
+        VPT_CUDA(c, cudaMalloc(&c->d_planeC, n_samples * sizeof(float4)));
+        c->cap_samples = n_samples;
+    }
+    if (need_planeD && !c->cap_planeD) {
+        VPT_CUDA(c, cudaMalloc(&c->d_planeD, c->cap_samples * sizeof(float4)));
+        c->cap_planeD = true;
+    }
+    return VPT_OK;
+}
+
+int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned n_passes, void* stream_) {
+    if (!c || !params) return fail(c, VPT_ERR_INVALID, "vpt_render_passes: null argument");
+    for (int i = 0; i < VPT_NUM_ARGS; ++i) if (!params[i]) return fail(c, VPT_ERR_INVALID, "vpt_render_passes: params[" + std::to_string(i) + "] is null");
+    if (n_passes == 0) return VPT_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+
+    vpt::FrameArgs fa;
+    memcpy(&fa.cam, params[VPT_ARG_CAMERA], sizeof(vpt_camera));
+    memcpy(&fa.lights, params[VPT_ARG_LIGHTS], sizeof(vpt_light_list));
+    memcpy(&fa.kp, params[VPT_ARG_KERNEL_PARAMS], sizeof(vpt_kernel_params));
+    vpt_devptr_t d_volumes, d_sphere, d_root;
+    memcpy(&d_volumes, params[VPT_ARG_VOLUMES], 8);
+    memcpy(&d_sphere, params[VPT_ARG_SPHERE], 8);
+    memcpy(&d_root, params[VPT_ARG_OCTREE], 8);
+    const vpt_kernel_params& kp = fa.kp;
+
+    if (kp.integrator != 0) return fail(c, VPT_ERR_UNSUPPORTED, "integrator != 0 (vol_integrator) is not implemented in this build");
+    if (kp.environment_type == 0 && kp.render && kp.iteration < kp.max_interactions)
+        return fail(c, VPT_ERR_UNSUPPORTED, "environment_type == 0 (Bruneton sky) is not implemented in this build; use an HDRI environment");
+    if (!d_volumes || !d_sphere || !d_root) return fail(c, VPT_ERR_INVALID, "volumes / sphere / octree device pointer is null");
+    if (!kp.accum_buffer || !kp.depth_buffer || !kp.cost_buffer || !kp.display_buffer || !kp.raw_buffer || !kp.blue_noise_buffer)
+        return fail(c, VPT_ERR_INVALID, "Kernel_params output buffer pointer is null");
+    if (kp.resolution.x == 0 || kp.resolution.y == 0) return fail(c, VPT_ERR_INVALID, "resolution is zero");
+
+    // scene tables (cached per pointer pair)
+    if (c->cached_volumes != d_volumes || c->cached_root != d_root) {
+        VPT_CUDA(c, vpt::launch_prepare_scene(reinterpret_cast<const vpt_gpu_vdb*>(d_volumes), reinterpret_cast<const vpt_octnode*>(d_root),
+                                              c->d_scene, c->d_internal, c->d_leaf_list, c->d_leaf_indices, c->d_vrec, VPT_OCT_MAX_VOLUMES, stream));
+        c->launches++;
+        c->cached_volumes = d_volumes; c->cached_root = d_root;
+    }
+
+    fa.sphere = reinterpret_cast<const vpt_sphere*>(d_sphere);
+    fa.scene = c->d_scene;
+    fa.geom = make_geom(c, kp.resolution.x, kp.resolution.y);
+
+    // how many of the requested passes actually sample (render_kernel.cu:2254)
+    unsigned n_sampled = 0;
+    if (kp.render && kp.iteration < kp.max_interactions) {
+        const unsigned left = kp.max_interactions - kp.iteration;
+        n_sampled = n_passes < left ? n_passes : left;
+    }
+
+    const int chunk = c->passes_per_chunk;
+    const bool planeD = (kp.environment_type == 0);
+    if (n_sampled) {
+        const size_t per_chunk = (size_t)fa.geom.n_local * (size_t)(n_sampled < (unsigned)chunk ? n_sampled : (unsigned)chunk);
+        int rc = ensure_frame_buffers(c, per_chunk, planeD);
+        if (rc != VPT_OK) return rc;
+    }
+    fa.queue = c->d_queue; fa.queue_count = c->d_counters; fa.queue_head = c->d_counters + 1;
+    fa.planeA = c->d_planeA; fa.planeB = c->d_planeB; fa.planeC = c->d_planeC; fa.planeD = planeD ? c->d_planeD : nullptr;
+
+    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : vpt::trace_max_ctas_per_sm(c->service_threshold);
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    const int trace_ctas = c->num_sms * ctas_per_sm;
+
+    const uint32_t it0 = kp.iteration;
+    unsigned done = 0;
+    while (done < n_sampled) {
+        const unsigned np = (n_sampled - done) < (unsigned)chunk ? (n_sampled - done) : (unsigned)chunk;
+        fa.kp.iteration = it0 + done;
+        VPT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned) * 2, stream));
+        VPT_CUDA(c, vpt::launch_generate(fa, (int)np, stream));          // reads the blue-noise state of pass `done`
+        VPT_CUDA(c, vpt::launch_trace(fa, trace_ctas, c->service_threshold, stream));
+        const bool last = (done + np == n_passes);
+        VPT_CUDA(c, vpt::launch_resolve(fa, (int)np, 1, last ? 1 : 0, stream));
+        VPT_CUDA(c, vpt::launch_bn_advance((void*)kp.blue_noise_buffer, (int)np, stream));
+        c->launches += 4;
+        done += np;
+    }
+    if (n_sampled < n_passes) {
+        // passes that no longer sample: WHITE / re-tonemap semantics of the kernel tail
+        fa.kp.iteration = it0 + n_sampled;
+        VPT_CUDA(c, vpt::launch_resolve(fa, (int)(n_passes - n_sampled), 0, 1, stream));
+        VPT_CUDA(c, vpt::launch_bn_advance((void*)kp.blue_noise_buffer, (int)(n_passes - n_sampled), stream));
+        c->launches += 2;
+    }
+    return VPT_OK;
+}
+
+int vpt_render_pass(vpt_context* c, void* const params[VPT_NUM_ARGS], void* stream) {
+    return vpt_render_passes(c, params, 1, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host-side scene helpers
+// ------------------------------------------------------------------------------------------------------
+int vpt_texture_create_3d(const float* host, int channels, int dx, int dy, int dz, vpt_tex_t* tex_out, void** array_out) {
+    if (!host || !tex_out || !array_out || (channels != 1 && channels != 4) || dx < 1 || dy < 1 || dz < 1)
+        return fail(nullptr, VPT_ERR_INVALID, "vpt_texture_create_3d: bad arguments");
+    cudaChannelFormatDesc desc = channels == 1 ? cudaCreateChannelDesc<float>() : cudaCreateChannelDesc<float4>();
+    cudaExtent ext = make_cudaExtent((size_t)dx, (size_t)dy, (size_t)dz);
+    cudaArray_t arr = nullptr;
+    VPT_CUDA(nullptr, cudaMalloc3DArray(&arr, &desc, ext));
+    cudaMemcpy3DParms cp; memset(&cp, 0, sizeof(cp));
+    const size_t esz = sizeof(float) * (size_t)channels;
+    cp.srcPtr = make_cudaPitchedPtr((void*)host, (size_t)dx * esz, (size_t)dx, (size_t)dy);
+    cp.dstArray = arr; cp.extent = ext; cp.kind = cudaMemcpyHostToDevice;
+    VPT_CUDA(nullptr, cudaMemcpy3D(&cp));
+    cudaResourceDesc res; memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray; res.res.array.array = arr;
+    cudaTextureDesc td; memset(&td, 0, sizeof(td));
+    td.normalizedCoords = 1; td.filterMode = cudaFilterModeLinear;
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t tex = 0;
+    VPT_CUDA(nullptr, cudaCreateTextureObject(&tex, &res, &td, NULL));
+    *tex_out = (vpt_tex_t)tex; *array_out = (void*)arr;
+    return VPT_OK;
+}
+
+int vpt_texture_create_env(const float* rgba, unsigned w, unsigned h, vpt_tex_t* tex_out, void** array_out) {
+    if (!rgba || !tex_out || !array_out || !w || !h) return fail(nullptr, VPT_ERR_INVALID, "vpt_texture_create_env: bad arguments");
+    const cudaChannelFormatDesc desc = cudaCreateChannelDesc<float4>();
+    cudaArray_t arr = nullptr;
+    VPT_CUDA(nullptr, cudaMallocArray(&arr, &desc, w, h));
+    VPT_CUDA(nullptr, cudaMemcpy2DToArray(arr, 0, 0, rgba, (size_t)w * sizeof(float4), (size_t)w * sizeof(float4), h, cudaMemcpyHostToDevice));
+    cudaResourceDesc res; memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray; res.res.array.array = arr;
+    cudaTextureDesc td; memset(&td, 0, sizeof(td));
+    td.addressMode[0] = cudaAddressModeWrap; td.addressMode[1] = cudaAddressModeClamp; td.addressMode[2] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 1;
+    cudaTextureObject_t tex = 0;
+    VPT_CUDA(nullptr, cudaCreateTextureObject(&tex, &res, &td, NULL));
+    *tex_out = (vpt_tex_t)tex; *array_out = (void*)arr;
+    return VPT_OK;
+}
+
+int vpt_texture_destroy(vpt_tex_t tex, void* array) {
+    if (tex) cudaDestroyTextureObject((cudaTextureObject_t)tex);
+    if (array) cudaFreeArray((cudaArray_t)array);
+    return VPT_OK;
+}
+
+void vpt_free(void* p) { free(p); }
+
+int vpt_vdb_load(const char* path, const char* grid_name, float** values_out, int info[13], float xform16[16], float stats[4]) {
+    if (!path || !grid_name || !values_out) return fail(nullptr, VPT_ERR_INVALID, "vpt_vdb_load: null argument");
+    *values_out = nullptr;
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return fail(nullptr, VPT_ERR_IO, std::string("vpt_vdb_load: cannot open ") + path);
+    std::vector<uint8_t> data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    vpt::VdbDenseGrid g;
+    try {
+        if (!vpt::vdb_read_dense(data.data(), data.size(), grid_name, g)) return 1;
+    } catch (const std::exception& e) { return fail(nullptr, VPT_ERR_IO, std::string("vpt_vdb_load: ") + e.what()); }
+    // cross-check against the file's own metadata (the only pin the format offers)
+    if (g.meta.has_file_bbox)
+        for (int a = 0; a < 3; ++a)
+            if (g.meta.file_bbox_min[a] != g.bbox_min[a] || g.meta.file_bbox_max[a] != g.bbox_max[a])
+                return fail(nullptr, VPT_ERR_IO, "vpt_vdb_load: decoded active bbox disagrees with file_bbox metadata");
+    if (g.meta.file_voxel_count >= 0 && (uint64_t)g.meta.file_voxel_count != g.active_leaf_voxels + g.active_tile_voxels)
+        return fail(nullptr, VPT_ERR_IO, "vpt_vdb_load: decoded active voxel count disagrees with file_voxel_count metadata");
+    const size_t nfl = g.values.size();
+    float* out = (float*)malloc(nfl * sizeof(float));
+    if (!out) return fail(nullptr, VPT_ERR_IO, "vpt_vdb_load: out of memory");
+    memcpy(out, g.values.data(), nfl * sizeof(float));
+    *values_out = out;
+    if (info) {
+        for (int a = 0; a < 3; ++a) { info[a] = g.dim[a]; info[3 + a] = g.bbox_min[a]; info[6 + a] = g.bbox_max[a]; }
+        info[9] = g.channels; info[10] = (int)g.leaf_count;
+        const uint64_t act = g.active_leaf_voxels + g.active_tile_voxels;
+        info[11] = (int)(act & 0xffffffffu); info[12] = (int)(act >> 32);
+    }
+    if (xform16) {
+        // convert_to_mat4: xform[i][j] = float(M(j, i)) with M the OpenVDB row-vector Mat4 => memory image m[c][r] = M[r][c]
+        for (int j = 0; j < 4; ++j) for (int i = 0; i < 4; ++i) xform16[i * 4 + j] = float(g.index_to_world[j * 4 + i]);
+    }
+    if (stats) {
+        float mx = 0.0f, mn = FLT_MAX;                      // VDB_INFO defaults then the scan of gpu_vdb.cpp:206-207 (first channel)
+        const size_t ch = (size_t)g.channels;
+        for (size_t i = 0; i < nfl; i += ch) { const float v = g.values[i]; mx = fmaxf(mx, v); mn = fminf(fmaxf(FLT_EPSILON, v), mn); }
+        stats[0] = mx; stats[1] = mn; stats[2] = (float)g.voxel_size[0]; stats[3] = g.background[0];
+    }
+    return VPT_OK;
+}
+
+int vpt_hdr_load(const char* path, float** rgba_out, unsigned* w, unsigned* h) {
+    if (!path || !rgba_out || !w || !h) return fail(nullptr, VPT_ERR_INVALID, "vpt_hdr_load: null argument");
+    std::vector<float> px; std::string err;
+    if (!vpt::load_hdr_float4(path, px, *w, *h, err)) return fail(nullptr, VPT_ERR_IO, "vpt_hdr_load: " + err);
+    *rgba_out = (float*)malloc(px.size() * sizeof(float)); memcpy(*rgba_out, px.data(), px.size() * sizeof(float));
+    return VPT_OK;
+}
+
+int vpt_bmp_load_rbg(const char* path, float** xyz_out, int* w, int* h) {
+    if (!path || !xyz_out || !w || !h) return fail(nullptr, VPT_ERR_INVALID, "vpt_bmp_load_rbg: null argument");
+    std::vector<float> px; std::string err;
+    if (!vpt::load_bmp_float3_rbg(path, px, *w, *h, err)) return fail(nullptr, VPT_ERR_IO, "vpt_bmp_load_rbg: " + err);
+    *xyz_out = (float*)malloc(px.size() * sizeof(float)); memcpy(*xyz_out, px.data(), px.size() * sizeof(float));
+    return VPT_OK;
+}
+
+int vpt_exr_load_rgb(const char* path, float** rgb_out, int* w, int* h) {
+    if (!path || !rgb_out || !w || !h) return fail(nullptr, VPT_ERR_INVALID, "vpt_exr_load_rgb: null argument");
+    std::vector<float> px; std::string err;
+    if (!vpt::load_exr_float3(path, px, *w, *h, err)) return fail(nullptr, VPT_ERR_IO, "vpt_exr_load_rgb: " + err);
+    *rgb_out = (float*)malloc(px.size() * sizeof(float)); memcpy(*rgb_out, px.data(), px.size() * sizeof(float));
+    return VPT_OK;
+}
+
+void vpt_volume_bounds(const vpt_gpu_vdb* v, float out6[6]) { vpt::instance_bounds_host(*v, out6); }
+
+int vpt_octree_build(const vpt_gpu_vdb* h_volumes, int n, vpt_devptr_t* d_root_out) {
+    if (!h_volumes || !d_root_out || n < 1) return fail(nullptr, VPT_ERR_INVALID, "vpt_octree_build: bad arguments");
+    if (n > VPT_OCT_MAX_VOLUMES) return fail(nullptr, VPT_ERR_UNSUPPORTED, "vpt_octree_build: more than 600 instances do not fit the reference OCTNode layout");
+    // root exactly as the reference host code builds it (union of instance bounds, +-1 world unit)
+    vpt_octnode* root = (vpt_octnode*)calloc(1, sizeof(vpt_octnode));
+    root->bbox.pmin = { 3.402823466e+38F, 3.402823466e+38F, 3.402823466e+38F };
+    root->bbox.pmax = { -3.402823466e+38F, -3.402823466e+38F, -3.402823466e+38F };
+    root->max_extinction = .0f; root->min_extinction = 3.402823466e+38F; root->voxel_size = 3.402823466e+38F;
+    root->depth = 4;
+    for (int i = 0; i < n; ++i) {
+        float b[6]; vpt::instance_bounds_host(h_volumes[i], b);
+        root->bbox.pmax.x = fmaxf(root->bbox.pmax.x, b[3]); root->bbox.pmax.y = fmaxf(root->bbox.pmax.y, b[4]); root->bbox.pmax.z = fmaxf(root->bbox.pmax.z, b[5]);
+        root->bbox.pmin.x = fminf(root->bbox.pmin.x, b[0]); root->bbox.pmin.y = fminf(root->bbox.pmin.y, b[1]); root->bbox.pmin.z = fminf(root->bbox.pmin.z, b[2]);
+        root->vol_indices[i] = i;
+        root->num_volumes++;
+        root->max_extinction = fmaxf(root->max_extinction, h_volumes[i].vdb_info.max_density);
+        root->min_extinction = fminf(root->min_extinction, h_volumes[i].vdb_info.min_density);
+        root->has_children = 1;
+    }
+    root->bbox.pmax.x += 1.0f; root->bbox.pmax.y += 1.0f; root->bbox.pmax.z += 1.0f;
+    root->bbox.pmin.x -= 1.0f; root->bbox.pmin.y -= 1.0f; root->bbox.pmin.z -= 1.0f;
+
+    vpt_octnode* d_nodes = nullptr; vpt_gpu_vdb* d_vols = nullptr;
+    cudaError_t e = cudaMalloc(&d_nodes, sizeof(vpt_octnode) * 585);
+    if (e == cudaSuccess) e = cudaMemset(d_nodes, 0, sizeof(vpt_octnode) * 585);
+    if (e == cudaSuccess) e = cudaMemcpy(d_nodes, root, sizeof(vpt_octnode), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&d_vols, sizeof(vpt_gpu_vdb) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpy(d_vols, h_volumes, sizeof(vpt_gpu_vdb) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = vpt::octree_build_device(d_nodes, d_vols, n, 0);
+    free(root);
+    cudaFree(d_vols);
+    if (e != cudaSuccess) { cudaFree(d_nodes); return fail(nullptr, VPT_ERR_CUDA, std::string("vpt_octree_build: ") + cudaGetErrorString(e)); }
+    *d_root_out = (vpt_devptr_t)(uintptr_t)d_nodes;
+    return VPT_OK;
+}
+
+int vpt_octree_destroy(vpt_devptr_t d_root) { if (d_root) cudaFree((void*)(uintptr_t)d_root); return VPT_OK; }
+
+void vpt_camera_look_at(vpt_camera* cam, const float lookfrom[3], const float lookat[3], const float vup[3], float vfov, float aspect, float aperture) {
+    auto sub = [](const float* a, const float* b, float* o) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; };
+    auto len = [](const float* a) { return sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); };
+    auto norm = [&](float* a) { const float inv = 1.0f / sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); a[0] *= inv; a[1] *= inv; a[2] *= inv; };
+    auto cross = [](const float* a, const float* b, float* o) { o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; };
+    memset(cam, 0, sizeof(*cam));
+    cam->time0 = .0f; cam->time1 = 1.0f;
+    float d[3]; sub(lookfrom, lookat, d);
+    const float focus = len(d);
+    cam->focus_dist = focus;
+    cam->lens_radius = aperture / 2.0f;
+    const float theta = vfov * float(M_PI) / 180.0f;
+    const float half_height = (float)tan(theta / 2.0f);
+    const float half_width = aspect * half_height;
+    float w[3] = { d[0], d[1], d[2] }; norm(w);
+    float u[3]; cross(vup, w, u); norm(u);
+    float v[3]; cross(w, u, v);
+    for (int a = 0; a < 3; ++a) {
+        (&cam->origin.x)[a] = lookfrom[a];
+        (&cam->u.x)[a] = u[a]; (&cam->v.x)[a] = v[a]; (&cam->w.x)[a] = w[a];
+        (&cam->lower_left_corner.x)[a] = lookfrom[a] - half_width * focus * u[a] - half_height * focus * v[a] - focus * w[a];
+        (&cam->horizontal.x)[a] = 2.0f * half_width * focus * u[a];
+        (&cam->vertical.x)[a] = 2.0f * half_height * focus * v[a];
+    }
+    cam->viz_dof = 0;
+}
+
+void vpt_kernel_params_defaults(vpt_kernel_params* kp) {
+    memset(kp, 0, sizeof(*kp));
+    kp->render = 1; kp->iteration = 0; kp->max_interactions = 100; kp->exposure_scale = 1.0f;
+    kp->environment_type = 0; kp->ray_depth = 50; kp->volume_depth = 1;
+    kp->phase_g1 = 0.0f; kp->phase_g2 = 0.0f; kp->phase_f = 1.0f; kp->tr_depth = 1.0f; kp->density_mult = 1.0f;
+    kp->albedo = {1.0f, 1.0f, 1.0f}; kp->extinction = {1.0f, 1.0f, 1.0f};
+    kp->azimuth = 120.0f; kp->elevation = 30.0f;            // ImGui values that overwrite 150/30 every frame (main.cpp:1420-1421, 1538-1539)
+    kp->sun_color = {1.0f, 1.0f, 1.0f}; kp->sun_mult = 1.0f;
+    kp->energy_inject = 1.0;                                 // main.cpp:1543 (energy == 0)
+    kp->sky_color = {1.0f, 1.0f, 1.0f}; kp->sky_mult = 1.0f;
+    kp->env_sample_tex_res = 360; kp->integrator = 0; kp->emission_scale = 0.0f; kp->emission_pivot = 1.0f;
+}
+
+} // extern "C"

@@ -1,0 +1,152 @@
+"""Render loop on top of the C ABI: the headless counterpart of the reference frame loop
+(source/main.cpp:1527-1860) -- fill Kernel_params, issue passes, keep `iteration`.
+
+`Renderer.render_pass()` is one reference launch (`vpt_render_pass`); `Renderer.render(n)` is n of them
+fused (`vpt_render_passes`).  `DistributedRenderer` shards the frame by interleaved row stripes over the
+ranks of a torch.distributed job, replicates the scene, and all-gathers the rank-local accumulators
+(one NCCL all-gather per call) before un-permuting them into a full frame.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+from ._native import lib, check
+from .scene import Scene, default_kernel_params
+
+
+class FrameBuffers:
+    """accum/cost (float3), depth (float), raw (float4), display (uint32) for `n_pixels` pixels."""
+
+    def __init__(self, n_pixels, device):
+        self.n = int(n_pixels)
+        self.accum = torch.zeros(self.n, 3, dtype=torch.float32, device=device)
+        self.cost = torch.zeros(self.n, 3, dtype=torch.float32, device=device)
+        self.depth = torch.zeros(self.n, dtype=torch.float32, device=device)
+        self.raw = torch.zeros(self.n, 4, dtype=torch.float32, device=device)
+        self.display = torch.zeros(self.n, dtype=torch.int32, device=device)
+
+    def zero_(self):
+        for t in (self.accum, self.cost, self.depth, self.raw, self.display):
+            t.zero_()
+
+    def bind(self, kp: N.Kernel_params):
+        kp.accum_buffer = self.accum.data_ptr(); kp.cost_buffer = self.cost.data_ptr(); kp.depth_buffer = self.depth.data_ptr()
+        kp.raw_buffer = self.raw.data_ptr(); kp.display_buffer = self.display.data_ptr()
+
+
+class LaunchParams:
+    """The `void* params[9]` array of main.cpp:1826, kept alive together with the values it points at."""
+
+    def __init__(self, scene: Scene, cam: N.camera, kp: N.Kernel_params):
+        self.cam, self.kp, self.scene = cam, kp, scene
+        self.lights = scene.lights
+        self.p_vol = C.c_uint64(scene.d_volumes.data_ptr())
+        self.p_sphere = C.c_uint64(scene.d_sphere.data_ptr())
+        self.p_geo = C.c_uint64(scene.d_geo_list.data_ptr())
+        self.p_bvh = C.c_uint64(scene.d_bvh.data_ptr())
+        self.p_oct = C.c_uint64(scene.d_oct_root)
+        self.atmos = scene.atmos
+        self.array = (C.c_void_p * 9)(
+            C.cast(C.byref(self.cam), C.c_void_p), C.cast(C.byref(self.lights), C.c_void_p),
+            C.cast(C.byref(self.p_vol), C.c_void_p), C.cast(C.byref(self.p_sphere), C.c_void_p),
+            C.cast(C.byref(self.p_geo), C.c_void_p), C.cast(C.byref(self.p_bvh), C.c_void_p),
+            C.cast(C.byref(self.p_oct), C.c_void_p), C.cast(C.byref(self.atmos), C.c_void_p),
+            C.cast(C.byref(self.kp), C.c_void_p))
+
+
+class Renderer:
+    def __init__(self, scene: Scene, width, height, cam: N.camera = None, kp: N.Kernel_params = None,
+                 rank=0, n_ranks=1, stripe_rows=16, options=None):
+        self.scene, self.width, self.height = scene, int(width), int(height)
+        self.ctx = C.c_void_p(0)
+        check(lib.vpt_create(C.byref(self.ctx)), None, "vpt_create")
+        check(lib.vpt_set_partition(self.ctx, rank, n_ranks, stripe_rows), self.ctx, "vpt_set_partition")
+        for k, v in (options or {}).items():
+            check(lib.vpt_set_option(self.ctx, k.encode(), int(v)), self.ctx, f"vpt_set_option({k})")
+        self.rank, self.n_ranks = rank, n_ranks
+        self.n_local = int(lib.vpt_local_pixels(self.ctx, self.width, self.height))
+        self.kp = kp if kp is not None else default_kernel_params()
+        self.kp.resolution = N.u2(self.width, self.height)
+        self.cam = cam if cam is not None else scene.frame_camera(self.width, self.height)
+        self.buffers = FrameBuffers(self.n_local, scene.device)
+        self.buffers.bind(self.kp)
+        self.kp.blue_noise_buffer = scene.d_blue_noise.data_ptr()
+        self.kp.emission_texture = scene.d_emission_lut.data_ptr()
+        self.kp.density_color_texture = scene.d_density_color.data_ptr()
+        if scene.env_tex is not None:
+            self.kp.env_tex = scene.env_tex.tex
+        self.params = LaunchParams(scene, self.cam, self.kp)
+
+    # -- the reference frame loop body: launch, ++iteration --
+    def render_pass(self, stream=None):
+        check(lib.vpt_render_pass(self.ctx, self.params.array, C.c_void_p(stream or 0)), self.ctx, "vpt_render_pass")
+        self.kp.iteration += 1
+
+    def render(self, n_passes, stream=None):
+        check(lib.vpt_render_passes(self.ctx, self.params.array, int(n_passes), C.c_void_p(stream or 0)), self.ctx, "vpt_render_passes")
+        self.kp.iteration += int(n_passes)
+
+    def reset(self):
+        self.kp.iteration = 0
+        self.buffers.zero_()
+        self.scene.reset_blue_noise()
+
+    def stats(self, with_queue=False):
+        n = C.c_ulonglong(0); q = C.c_uint(0)
+        check(lib.vpt_get_stats(self.ctx, C.byref(n), C.byref(q) if with_queue else None), self.ctx, "vpt_get_stats")
+        return int(n.value), int(q.value)
+
+    def accum_image(self):
+        """(H, W, 3) float32 linear radiance (single rank only)."""
+        assert self.n_ranks == 1
+        return self.buffers.accum.view(self.height, self.width, 3)
+
+    def unpermute(self, gathered: torch.Tensor, elem_floats: int):
+        full = torch.empty(self.height * self.width, elem_floats, dtype=gathered.dtype, device=gathered.device)
+        check(lib.vpt_unpermute(self.ctx, C.c_void_p(gathered.data_ptr()), C.c_void_p(full.data_ptr()), self.width, self.height,
+                                4 * elem_floats, C.c_void_p(0)), self.ctx, "vpt_unpermute")
+        return full
+
+    def close(self):
+        if self.ctx:
+            lib.vpt_destroy(self.ctx); self.ctx = C.c_void_p(0)
+
+
+class DistributedRenderer:
+    """Frame sharded over torch.distributed ranks (one process per GPU); scene replicated on each.
+
+    Pixels are independent and every Philox stream is keyed by the GLOBAL pixel index, so the gathered
+    frame is bit-identical to a single-GPU render whatever the partition."""
+
+    def __init__(self, scene: Scene, width, height, cam=None, kp=None, stripe_rows=16, options=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.r = Renderer(scene, width, height, cam=cam, kp=kp, rank=self.rank, n_ranks=self.world,
+                          stripe_rows=stripe_rows, options=options)
+        self.gathered = torch.empty(self.world * self.r.n_local, 3, dtype=torch.float32, device=scene.device)
+
+    def render(self, n_passes):
+        self.r.render(n_passes)
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.gathered, self.r.buffers.accum)     # the one collective of the path
+        else:
+            self.gathered.copy_(self.r.buffers.accum)
+
+    def full_accum(self):
+        return self.r.unpermute(self.gathered, 3).view(self.r.height, self.r.width, 3)
+
+
+def stripe_rows_of_rank(height, rank, n_ranks, stripe_rows):
+    """Host-side mirror of the kernel's local-row -> global-row map (used by the CPU/gloo tests)."""
+    if n_ranks == 1:
+        return np.arange(height)
+    stripes = (height + stripe_rows - 1) // stripe_rows
+    per_rank = (stripes + n_ranks - 1) // n_ranks
+    rows = []
+    for lr in range(per_rank * stripe_rows):
+        s = lr // stripe_rows
+        rows.append((s * n_ranks + rank) * stripe_rows + lr % stripe_rows)
+    return np.array(rows)

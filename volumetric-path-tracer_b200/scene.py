@@ -1,0 +1,337 @@
+"""Headless scene set-up: the host work `source/main.cpp` does before its frame loop.
+
+Builds, with the library's own loaders and builders (no reference code involved):
+  * GPU_VDB instances from .vdb files or dense numpy grids   (gpu_vdb.cpp:105-472 -> vpt_vdb_load + vpt_texture_create_3d)
+  * `.ins` style instancing transforms                        (main.cpp:1059-1099)
+  * the depth-3 instance octree in the reference node layout  (bvh_builder.cpp:61-96 -> vpt_octree_build)
+  * environment map, blue-noise buffer, blackbody / density-colour LUTs, reference sphere
+  * the nine launch parameters of `volume_rt_kernel`          (main.cpp:1826)
+Device memory is held in torch tensors (plumbing only); textures are CUDA arrays made by the library.
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _native as N
+from ._native import lib, check
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ASSET_DIRS = [os.path.join(_REPO, "tests", "golden", "assets"), os.path.join(_REPO, "oracle", "_ref", "assets")]
+
+
+def find_asset(name):
+    for d in ASSET_DIRS:
+        p = os.path.join(d, name)
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def _dev_bytes(buf: bytes, device):
+    t = torch.empty(max(len(buf), 1), dtype=torch.uint8, device=device)
+    if len(buf):
+        t.copy_(torch.frombuffer(bytearray(buf), dtype=torch.uint8))
+    return t
+
+
+class Texture:
+    def __init__(self, tex, array):
+        self.tex, self.array = int(tex), array
+
+    def destroy(self):
+        if self.tex:
+            lib.vpt_texture_destroy(self.tex, self.array)
+            self.tex, self.array = 0, None
+
+
+def texture_3d(data: np.ndarray) -> Texture:
+    """data: (z, y, x) float32 or (z, y, x, 4) float32."""
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    ch = 1 if data.ndim == 3 else data.shape[3]
+    dz, dy, dx = data.shape[:3]
+    tex, arr = C.c_uint64(0), C.c_void_p(0)
+    check(lib.vpt_texture_create_3d(data.ctypes.data_as(C.POINTER(C.c_float)), ch, dx, dy, dz, C.byref(tex), C.byref(arr)),
+          None, "vpt_texture_create_3d")
+    return Texture(tex.value, arr)
+
+
+def texture_env(rgba: np.ndarray) -> Texture:
+    rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+    h, w = rgba.shape[:2]
+    tex, arr = C.c_uint64(0), C.c_void_p(0)
+    check(lib.vpt_texture_create_env(rgba.ctypes.data_as(C.POINTER(C.c_float)), w, h, C.byref(tex), C.byref(arr)), None, "vpt_texture_create_env")
+    return Texture(tex.value, arr)
+
+
+def load_vdb_grid(path, grid):
+    """-> (values (z,y,x[,3]) float32, info dict) or None when the grid is absent."""
+    vals = C.POINTER(C.c_float)()
+    info = (C.c_int * 13)(); xf = (C.c_float * 16)(); st = (C.c_float * 4)()
+    rc = lib.vpt_vdb_load(path.encode(), grid.encode(), C.byref(vals), info, xf, st)
+    if rc == 1:
+        return None
+    check(rc, None, f"vpt_vdb_load({path}, {grid})")
+    dx, dy, dz = info[0], info[1], info[2]
+    ch = info[9]
+    n = dx * dy * dz * ch
+    arr = np.ctypeslib.as_array(vals, shape=(n,)).copy()
+    lib.vpt_free(vals)
+    arr = arr.reshape((dz, dy, dx) if ch == 1 else (dz, dy, dx, ch))
+    meta = dict(dim=(dx, dy, dz), bbox_min=(info[3], info[4], info[5]), bbox_max=(info[6], info[7], info[8]), channels=ch,
+                leaf_count=info[10], active_voxels=(info[11] & 0xffffffff) | (info[12] << 32),
+                xform=np.array(list(xf), dtype=np.float32).reshape(4, 4), max_value=st[0], min_density=st[1],
+                voxel_size=st[2], background=st[3])
+    return arr, meta
+
+
+def load_hdr(path):
+    px = C.POINTER(C.c_float)(); w = C.c_uint(0); h = C.c_uint(0)
+    check(lib.vpt_hdr_load(path.encode(), C.byref(px), C.byref(w), C.byref(h)), None, "vpt_hdr_load")
+    a = np.ctypeslib.as_array(px, shape=(h.value, w.value, 4)).copy()
+    lib.vpt_free(px)
+    return a
+
+
+def load_bmp_rbg(path):
+    px = C.POINTER(C.c_float)(); w = C.c_int(0); h = C.c_int(0)
+    check(lib.vpt_bmp_load_rbg(path.encode(), C.byref(px), C.byref(w), C.byref(h)), None, "vpt_bmp_load_rbg")
+    a = np.ctypeslib.as_array(px, shape=(h.value, w.value, 3)).copy()
+    lib.vpt_free(px)
+    return a
+
+
+def load_exr_rgb(path):
+    px = C.POINTER(C.c_float)(); w = C.c_int(0); h = C.c_int(0)
+    check(lib.vpt_exr_load_rgb(path.encode(), C.byref(px), C.byref(w), C.byref(h)), None, "vpt_exr_load_rgb")
+    a = np.ctypeslib.as_array(px, shape=(h.value, w.value, 3)).copy()
+    lib.vpt_free(px)
+    return a
+
+
+# ---- reference mat4 algebra (m[col][row] memory image), float32, no FMA ------------------------------
+def mat4_identity():
+    return np.eye(4, dtype=np.float32)
+
+
+def mat4_mul_ref(A, B):
+    """The reference's `mat4::operator*(mat4)` (matrix_math.h:130-162): with a_rc = A.m[c][r] it stores
+    ret.m[r][c] = sum_k a_rk * b_kc -- i.e. the memory image of the result is (A^T_mem ... ) as coded, not a
+    textbook product; reproduced literally so instance transforms match."""
+    a = A.T.astype(np.float32)   # a[r][c] = A.m[c][r]
+    b = B.T.astype(np.float32)
+    R = np.zeros((4, 4), dtype=np.float32)
+    for r in range(4):
+        for c in range(4):
+            acc = np.float32(a[r][0] * b[0][c])
+            for k in range(1, 4):
+                acc = np.float32(acc + np.float32(a[r][k] * b[k][c]))
+            R[r][c] = acc            # ret[r][c] = ret.m[r][c]
+    return R
+
+
+def quaternion_to_mat4(x, y, z, w):
+    """matrix_math.h:378-412 (double overload; normalisation uses sqrtf)."""
+    n = 1.0 / float(np.sqrt(np.float32(x * x + y * y + z * z + w * w)))
+    x, y, z, w = x * n, y * n, z * n, w * n
+    f = np.float32
+    m11, m12, m13 = f(1.0 - 2.0 * y * y - 2.0 * z * z), f(2.0 * x * y + 2.0 * z * w), f(2.0 * x * z - 2.0 * y * w)
+    m21, m22, m23 = f(2.0 * x * y - 2.0 * z * w), f(1.0 - 2.0 * x * x - 2.0 * z * z), f(2.0 * y * z + 2.0 * x * w)
+    m31, m32, m33 = f(2.0 * x * z + 2.0 * y * w), f(2.0 * y * z - 2.0 * x * w), f(1.0 - 2.0 * x * x - 2.0 * y * y)
+    M = np.zeros((4, 4), dtype=np.float32)
+    # mat4(m11..m44) stores m[0][0]=m11, m[1][0]=m12, m[2][0]=m13, m[3][0]=m14, m[0][1]=m21, ...
+    rows = [[m11, m12, m13, 0.0], [m21, m22, m23, 0.0], [m31, m32, m33, 0.0], [0.0, 0.0, 0.0, 1.0]]
+    for r in range(4):
+        for c in range(4):
+            M[c][r] = rows[r][c]
+    return M
+
+
+def instance_xform(base_xform, pos, quat, scale):
+    """main.cpp:1066-1097: zero the translation, scale the diagonal, rotate, translate."""
+    X = np.array(base_xform, dtype=np.float32).copy()
+    X[0][3] = X[1][3] = X[2][3] = np.float32(0.0)
+    s = np.float32(scale)
+    X[0][0] *= s; X[1][1] *= s; X[2][2] *= s
+    R = quaternion_to_mat4(*[float(q) for q in quat])
+    X = mat4_mul_ref(R, X)
+    X[0][3] += np.float32(pos[0]); X[1][3] += np.float32(pos[1]); X[2][3] += np.float32(pos[2])
+    return X
+
+
+class Volume:
+    """One unique VDB: textures + the GPU_VDB record the kernels read (GPU_VDB::loadVDB, gpu_vdb.cpp:105-472)."""
+
+    def __init__(self):
+        self.textures = []
+        self.rec = N.GPU_VDB()
+
+    @staticmethod
+    def from_dense(density: np.ndarray, bbox_min=(0, 0, 0), xform=None, voxelsize=1.0, emission=None, color=None):
+        v = Volume()
+        dz, dy, dx = density.shape
+        info = v.rec.vdb_info
+        info.voxelsize = float(voxelsize)
+        info.dim = N.i3(dx, dy, dz)
+        info.bmin = N.f3(*[float(b) for b in bbox_min])
+        info.bmax = N.f3(float(bbox_min[0] + dx - 1), float(bbox_min[1] + dy - 1), float(bbox_min[2] + dz - 1))
+        d32 = np.ascontiguousarray(density, dtype=np.float32)
+        # max/min rule of gpu_vdb.cpp:206-207 (VDB_INFO defaults 0 / FLT_MAX): min over max(FLT_EPSILON, v) -- quirk Q10
+        info.max_density = float(max(np.float32(0.0), d32.max()))
+        info.min_density = float(np.minimum(np.maximum(np.float32(np.finfo(np.float32).eps), d32), np.float32(3.4028235e38)).min())
+        t = texture_3d(d32); v.textures.append(t); info.density_texture = t.tex
+        if emission is not None:
+            t = texture_3d(np.ascontiguousarray(emission, dtype=np.float32)); v.textures.append(t)
+            info.emission_texture = t.tex; info.has_emission = 1
+        if color is not None:
+            c4 = np.zeros(color.shape[:3] + (4,), dtype=np.float32); c4[..., :3] = color[..., :3]; c4[..., 3] = 1.0
+            t = texture_3d(c4); v.textures.append(t)
+            info.color_texture = t.tex; info.has_color = 1
+        X = mat4_identity() if xform is None else np.array(xform, dtype=np.float32)
+        for a in range(4):
+            for b in range(4):
+                v.rec.xform[a][b] = float(X[a][b])
+        return v
+
+    @staticmethod
+    def load_vdb(path, density="density", emission="heat", color="Cd"):
+        got = load_vdb_grid(path, density)
+        if got is None:
+            raise N.VptError(f"{path}: no grid named {density!r}")
+        dens, meta = got
+        em = load_vdb_grid(path, emission) if emission else None
+        cd = load_vdb_grid(path, color) if color else None
+        v = Volume.from_dense(dens, bbox_min=meta["bbox_min"], xform=meta["xform"], voxelsize=meta["voxel_size"],
+                              emission=None if em is None else em[0], color=None if cd is None else cd[0])
+        # bmax is the inclusive index bbox max (gpu_vdb.cpp:453-455)
+        v.rec.vdb_info.bmax = N.f3(*[float(b) for b in meta["bbox_max"]])
+        v.meta = meta
+        return v
+
+    def instance(self, pos=(0, 0, 0), quat=(0, 0, 0, 1), scale=1.0) -> N.GPU_VDB:
+        g = N.GPU_VDB()
+        C.memmove(C.byref(g), C.byref(self.rec), C.sizeof(N.GPU_VDB))
+        base = np.array([[self.rec.xform[a][b] for b in range(4)] for a in range(4)], dtype=np.float32)
+        X = instance_xform(base, pos, quat, scale)
+        for a in range(4):
+            for b in range(4):
+                g.xform[a][b] = float(X[a][b])
+        return g
+
+
+def synthetic_env(width=3000, height=1500):
+    """Procedural HDR sky of the reference HDRI's shape, used only when the asset is not on the box."""
+    v = np.linspace(0.0, 1.0, height, dtype=np.float32)[:, None]
+    u = np.linspace(0.0, 1.0, width, dtype=np.float32)[None, :]
+    sky = 0.25 + 0.75 * (1.0 - v) ** 2
+    sun = 40.0 * np.exp(-((u - 0.3) ** 2 + (v - 0.25) ** 2) / 0.0005)
+    rgba = np.zeros((height, width, 4), dtype=np.float32)
+    rgba[..., 0] = 0.6 * sky + sun; rgba[..., 1] = 0.75 * sky + 0.9 * sun; rgba[..., 2] = 1.0 * sky + 0.8 * sun
+    return rgba
+
+
+def synthetic_blue_noise():
+    rng = np.random.RandomState(1234)
+    return rng.rand(256, 256, 3).astype(np.float32)
+
+
+class Scene:
+    """Everything the nine launch parameters point at (main.cpp:1299-1313, 1378-1403, 1480-1502)."""
+
+    def __init__(self, instances, device="cuda:0", env="Barce_Rooftop_C_3k.hdr", lights=None, keep=None):
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.keep = keep or []
+        self.instances = list(instances)
+        n = len(self.instances)
+        arr = (N.GPU_VDB * n)(*self.instances)
+        self.h_volumes = arr
+        self.d_volumes = _dev_bytes(bytes(arr), self.device)
+        root = C.c_uint64(0)
+        check(lib.vpt_octree_build(arr, n, C.byref(root)), None, "vpt_octree_build")
+        self.d_oct_root = root.value
+        self.own_octree = True
+        # reference sphere (main.cpp:1480-1488)
+        sp = N.sphere(); sp.center = N.f3(0, 1000, 0); sp.radius = 1.0; sp.color = N.f3(10.0, 0, 0); sp.roughness = 1.0
+        self.h_sphere = sp
+        self.d_sphere = _dev_bytes(bytes(sp), self.device)
+        self.d_geo_list = _dev_bytes(bytes(N.geometry_list()), self.device)
+        self.d_bvh = _dev_bytes(bytes(N.BVHNode()), self.device)
+        # lights (managed memory in the reference; plain device memory is equivalent for the kernels)
+        self.lights = N.light_list()
+        if lights:
+            pl = (N.point_light * len(lights))()
+            for i, (pos, col, power) in enumerate(lights):
+                pl[i].pos = N.f3(*pos); pl[i].color = N.f3(*col); pl[i].power = float(power)
+            self.d_lights = _dev_bytes(bytes(pl), self.device)
+            self.lights.num_lights = len(lights); self.lights.light_ptr = self.d_lights.data_ptr()
+        # blue noise (fileIO.cpp:460-495), LUTs (main.cpp:1389-1402)
+        p = find_asset("BN0.bmp")
+        bn = load_bmp_rbg(p) if p else synthetic_blue_noise()
+        self.data_notes = [] if p else ["blue noise: synthetic (BN0.bmp not found)"]
+        self.bn_host = np.ascontiguousarray(bn.reshape(-1, 3), dtype=np.float32)
+        self.d_blue_noise = torch.from_numpy(self.bn_host.copy()).to(self.device)
+        p = find_asset("blackbody_texture.exr")
+        bb = load_exr_rgb(p).reshape(-1, 3) if p else np.linspace(0, 1, 256, dtype=np.float32)[:, None].repeat(3, 1)
+        self.d_emission_lut = torch.from_numpy(np.ascontiguousarray(bb, dtype=np.float32)).to(self.device)
+        p = find_asset("density_color_texture2.exr")
+        dc = load_exr_rgb(p).reshape(-1, 3) if p else np.ones((256, 3), dtype=np.float32)
+        self.d_density_color = torch.from_numpy(np.ascontiguousarray(dc, dtype=np.float32)).to(self.device)
+        # environment (main.cpp:945-978)
+        self.env_tex = None
+        if env is not None:
+            if isinstance(env, np.ndarray):
+                rgba = env
+            else:
+                p = find_asset(env)
+                if p:
+                    rgba = load_hdr(p)
+                else:
+                    rgba = synthetic_env(); self.data_notes.append(f"environment: synthetic 3000x1500 ({env} not found)")
+            self.env_tex = texture_env(rgba)
+        # atmosphere block: the render path with an HDRI never reads the LUTs, but the reference kernel still
+        # issues two (dead) fetches from them in estimate_sun, so give it valid 1-texel textures
+        self.atmos = N.AtmosphereParameters()
+        self._dummy2d = texture_env(np.zeros((1, 1, 4), dtype=np.float32))
+        self._dummy3d = texture_3d(np.zeros((1, 1, 1, 4), dtype=np.float32))
+        self.atmos.transmittance_texture = self._dummy2d.tex; self.atmos.irradiance_texture = self._dummy2d.tex
+        self.atmos.scattering_texture = self._dummy3d.tex; self.atmos.single_mie_scattering_texture = self._dummy3d.tex
+        self.atmos.bottom_radius = 6360.0; self.atmos.top_radius = 6420.0
+
+    def reset_blue_noise(self):
+        self.d_blue_noise.copy_(torch.from_numpy(self.bn_host))
+
+    def world_bounds(self):
+        """bbox used by the F-key framing (main.cpp:525-543): min/max with the origin included."""
+        lo = np.zeros(3, dtype=np.float32); hi = np.zeros(3, dtype=np.float32)
+        for g in self.instances:
+            X = np.array([[g.xform[a][b] for b in range(4)] for a in range(4)], dtype=np.float32)
+            for corner, agg in ((g.vdb_info.bmin, "lo"), (g.vdb_info.bmax, "hi")):
+                p = np.array([corner.x, corner.y, corner.z, 1.0], dtype=np.float32)
+                w = np.array([np.dot(X[r], p) for r in range(3)], dtype=np.float32)   # xform.transpose().transform_point
+                if agg == "lo": lo = np.minimum(lo, w)
+                else: hi = np.maximum(hi, w)
+        return lo, hi
+
+    def frame_camera(self, width, height, fov=30.0, aperture=0.0) -> N.camera:
+        lo, hi = self.world_bounds()
+        center = (hi + lo) / np.float32(2)
+        dist = float(np.linalg.norm(hi - lo))
+        lookfrom = center + np.float32(dist)
+        cam = N.camera()
+        lib.vpt_camera_look_at(C.byref(cam), N.fvec(lookfrom), N.fvec(center), N.fvec((0, 1, 0)), float(fov), float(width) / float(height), float(aperture))
+        return cam
+
+    def destroy(self):
+        if self.own_octree and self.d_oct_root:
+            lib.vpt_octree_destroy(self.d_oct_root); self.d_oct_root = 0
+        for t in (self.env_tex, self._dummy2d, self._dummy3d):
+            if t: t.destroy()
+
+
+def default_kernel_params() -> N.Kernel_params:
+    kp = N.Kernel_params()
+    lib.vpt_kernel_params_defaults(C.byref(kp))
+    return kp
