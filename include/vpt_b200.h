@@ -46,7 +46,7 @@ int  vpt_abi_sizes(size_t* out, int n);
 
 /* Tunables: "passes_per_chunk" (1..64, passes fused per generate/trace/resolve round, default 8),
  * "service_threshold" (8|16|20|24|32 lanes that must be inside a walk to keep the step loop running),
- * "ctas_per_sm" (0 = occupancy maximum). */
+ * "ctas_per_sm" (0 = occupancy maximum), "count_stats" / "profile" (0|1, see vpt_get_counters / vpt_get_kernel_times). */
 int  vpt_set_option(vpt_context* ctx, const char* key, int value);
 
 /* Multi-GPU partition of the frame: rank r of n renders the interleaved row stripes r, r+n, ... of
@@ -80,6 +80,13 @@ int  vpt_invalidate_scene(vpt_context* ctx);
  * synchronised by the caller) rays pushed into the hit queue by the final chunk. */
 int  vpt_get_stats(vpt_context* ctx, unsigned long long* kernel_launches_total, unsigned* last_queue_count);
 
+/* Instrumentation.  Option "count_stats" = 1 makes the trace kernel accumulate out[0] volume lookups,
+ * out[1] lane-steps, out[2] warp step-loop iterations, out[3] lane transitions, out[4] warp transition rounds
+ * (SIMT efficiency of the step loop = out[1] / (32 * out[2])).  Option "profile" = 1 brackets every kernel with
+ * CUDA events: ms/n[0..3] = generate, trace, resolve, blue-noise advance.  Both calls synchronise the device. */
+int  vpt_get_counters(vpt_context* ctx, unsigned long long out[8], int reset);
+int  vpt_get_kernel_times(vpt_context* ctx, float ms[4], int n[4]);
+
 /* ---- host-side scene helpers (what the reference does in main.cpp / gpu_vdb.cpp / bvh_builder.cpp) -- */
 
 /* Dense grid -> 3-D texture, as GPU_VDB::loadVDB builds them (gpu_vdb.cpp:215-248: cudaArray, normalised
@@ -109,6 +116,9 @@ void vpt_free(void* p);
  * *d_root_out: device pointer to node 0 of a contiguous 585-node array (free with vpt_octree_destroy). */
 int  vpt_octree_build(const vpt_gpu_vdb* h_volumes, int n, vpt_devptr_t* d_root_out);
 int  vpt_octree_destroy(vpt_devptr_t d_root);
+/* Copy any pointer-linked octree (this builder's or the reference's device-heap one) into 585 host nodes in the
+ * canonical numbering 0 | 1+c1 | 9+c1*8+c2 | 73+c1*64+c2*8+c3; exists[j] = 0 for nodes never allocated. */
+int  vpt_octree_read(vpt_devptr_t d_root, vpt_octnode* h_nodes585, int* h_exists585);
 /* AABB of one instance (GPU_VDB::Bounds, gpu_vdb.h:131-146): out6 = pmin, pmax. */
 void vpt_volume_bounds(const vpt_gpu_vdb* h_volume, float out6[6]);
 

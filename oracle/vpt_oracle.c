@@ -1,0 +1,546 @@
+/*
+ * vpt_oracle.c -- TEST INFRASTRUCTURE: plain-C CPU restatement of the reference render pass.
+ *
+ * Restates, function by function, the live code of source/render_kernel.cu (direct integrator,
+ * `volume_rt_kernel` :2216-2326) so that the algorithm can be checked on a machine without a GPU and
+ * timed as the CPU baseline ("port").  Each function cites the reference lines it follows.
+ *
+ * Parity status: PINNED BY REFERENCE EXECUTION, NOT BY THE REFERENCE'S OWN TESTS.  The reference ships no
+ * golden vectors for this path; tests/golden/*.npz hold outputs of the reference's own
+ * kernel (oracle/_ref, built from /root/reference) and this file is checked against them.  Agreement
+ * is statistical, not per-seed: the GPU path samples volumes with hardware trilinear filtering (8-bit
+ * weights) and --use_fast_math intrinsics, which C on a CPU reproduces only approximately, and the
+ * estimator is chaotic (one flipped accept/reject decision changes a pixel's sample).  The per-seed
+ * oracle is the reference kernel itself (tests/oracle_ref.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this library.
+ * The product (libvpt_b200.so) never links, calls or falls back to it.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+#include "../include/vpt_abi.h"
+
+typedef struct { float x, y, z; } v3;
+static inline v3 V(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+static inline v3 add(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline v3 sub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline v3 mul(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline v3 scl(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
+static inline v3 divv(v3 a, v3 b) { return V(a.x / b.x, a.y / b.y, a.z / b.z); }
+static inline float dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline float len(v3 a) { return sqrtf(dot(a, a)); }
+static inline v3 nrm(v3 a) { return scl(a, 1.0f / sqrtf(dot(a, a))); }
+static inline v3 crs(v3 a, v3 b) { return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+static inline v3 lerp3(v3 a, v3 b, float t) { return add(a, scl(sub(b, a), t)); }
+static inline float clampf(float f, float a, float b) { return fmaxf(a, fminf(f, b)); }
+static inline int is_black(v3 v) { return len(v) < 1.192092896e-07F; }
+static inline v3 from3(vpt_f3 a) { return V(a.x, a.y, a.z); }
+
+#define EPS 0.001f
+#define M_INF_F 3.402823466e+38F
+#define PI_F 3.14159265358979323846f
+
+/* ---- Philox4x32-10 stream of the reference (curand_init(idx, 0, iteration*4096)) ---- */
+typedef struct { uint32_t key, base, k, cached; uint32_t blk[4]; } rng_t;
+static void philox(uint32_t c0, uint32_t c1, uint32_t key, uint32_t out[4]) {
+    uint32_t x0 = c0, x1 = c1, x2 = 0, x3 = 0, k0 = key, k1 = 0;
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * x0, p1 = (uint64_t)0xCD9E8D57u * x2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ x1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ x3 ^ k1, n3 = (uint32_t)p0;
+        x0 = n0; x1 = n1; x2 = n2; x3 = n3; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
+}
+static void rng_init(rng_t* r, uint32_t idx, uint32_t iteration) { r->key = idx; r->base = (iteration * 4096u) >> 2; r->k = 0; r->cached = 0xffffffffu; }
+static float rnd(rng_t* r) {
+    uint32_t b = r->k >> 2;
+    if (b != r->cached) { uint32_t c0 = r->base + b; philox(c0, c0 < r->base ? 1u : 0u, r->key, r->blk); r->cached = b; }
+    uint32_t v = r->blk[r->k & 3u]; r->k++;
+    return (float)v * 2.3283064e-10f + 1.1641532e-10f;             /* curand_uniform.h:69-72 */
+}
+
+/* ---- scene description handed over by the Python test harness ---------------------------------- */
+typedef struct {
+    int dim[3]; float bmin[3], bmax[3]; float xform[16];           /* GPU_VDB memory image m[a][b] */
+    float max_density, min_density, voxelsize;
+    const float* density;                                          /* dim x*y*z, x fastest */
+    const float* emission; int edim[3];                            /* optional heat grid (own dims, quirk Q8) */
+    const float* color4;  int cdim[3];                             /* optional Cd grid, float4 */
+    float inv[12];                                                 /* filled by orc_prepare: world -> index affine rows */
+} orc_volume;
+
+typedef struct {
+    int n_volumes; orc_volume* volumes;
+    const float* env_rgba; int env_w, env_h;
+    const float* emission_lut; const float* density_color_lut;     /* 256 x float3 */
+    float sph_center[3], sph_radius, sph_color[3], sph_roughness;
+    int n_lights; const float* lights;                             /* pos[3] color[3] power */
+    /* octree (filled by orc_prepare) */
+    float node_min[585][3], node_max[585][3]; int node_nvol[585]; int node_exists[585];
+    int* leaf_lists;                                               /* 512 x (1 + 600) ints */
+    float root_max_ext, root_min_ext;
+} orc_scene;
+
+/* ---- 4x4 inverse of xform.transpose() (matrix_math.h:215-252), in double for stability ----------- */
+static void invert_transposed(const float X[16], float out[12]) {
+    double n[4][4];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) n[r][c] = X[r * 4 + c];   /* transpose().m[c][r] => n_rc = X[r][c] */
+    double inv[4][4], a[4][8];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { a[r][c] = n[r][c]; a[r][4 + c] = r == c; }
+    for (int i = 0; i < 4; ++i) {
+        int p = i; for (int r = i + 1; r < 4; ++r) if (fabs(a[r][i]) > fabs(a[p][i])) p = r;
+        for (int c = 0; c < 8; ++c) { double t = a[i][c]; a[i][c] = a[p][c]; a[p][c] = t; }
+        double d = a[i][i]; for (int c = 0; c < 8; ++c) a[i][c] /= d;
+        for (int r = 0; r < 4; ++r) if (r != i) { double f = a[r][i]; for (int c = 0; c < 8; ++c) a[r][c] -= f * a[i][c]; }
+    }
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) inv[r][c] = a[r][4 + c];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) out[r * 4 + c] = (float)inv[r][c];
+}
+
+static void vol_bounds(const orc_volume* g, float lo[3], float hi[3]) {               /* GPU_VDB::Bounds, gpu_vdb.h:131-146 */
+    float c[3], e[3];
+    for (int a = 0; a < 3; ++a) { c[a] = (g->bmax[a] + g->bmin[a]) * 0.5f; e[a] = (g->bmax[a] - g->bmin[a]) * 0.5f; }
+    for (int r = 0; r < 3; ++r) {
+        const float* X = g->xform + 4 * r;
+        float nc = X[0] * c[0] + X[1] * c[1] + X[2] * c[2] + X[3];
+        float ne = fabsf(X[0]) * e[0] + fabsf(X[1]) * e[1] + fabsf(X[2]) * e[2];
+        lo[r] = nc - ne; hi[r] = nc + ne;
+    }
+}
+
+static void child_box(int idx, const float pmin[3], const float pmax[3], float cmin[3], float cmax[3]) {   /* divide_bbox */
+    float h[3]; for (int a = 0; a < 3; ++a) h[a] = (float)((pmin[a] + pmax[a]) * 0.5);
+    int xp = idx & 1, ym = idx & 2, zp = idx & 4;
+    cmin[0] = xp ? h[0] : pmin[0]; cmax[0] = xp ? pmax[0] : h[0];
+    cmin[1] = ym ? pmin[1] : h[1]; cmax[1] = ym ? h[1] : pmax[1];
+    cmin[2] = zp ? h[2] : pmin[2]; cmax[2] = zp ? pmax[2] : h[2];
+}
+
+/* node numbering: 0 root, 1+c1, 9+c1*8+c2, 73+c1*64+c2*8+c3 */
+int orc_prepare(orc_scene* s) {
+    if (s->n_volumes < 1 || s->n_volumes > 600) return -1;
+    float (*blo)[3] = malloc(sizeof(float[3]) * s->n_volumes), (*bhi)[3] = malloc(sizeof(float[3]) * s->n_volumes);
+    float rmin[3] = { M_INF_F, M_INF_F, M_INF_F }, rmax[3] = { -M_INF_F, -M_INF_F, -M_INF_F };
+    s->root_max_ext = 0.f; s->root_min_ext = M_INF_F;
+    for (int v = 0; v < s->n_volumes; ++v) {
+        invert_transposed(s->volumes[v].xform, s->volumes[v].inv);
+        vol_bounds(&s->volumes[v], blo[v], bhi[v]);
+        for (int a = 0; a < 3; ++a) { rmin[a] = fminf(rmin[a], blo[v][a]); rmax[a] = fmaxf(rmax[a], bhi[v][a]); }
+        s->root_max_ext = fmaxf(s->root_max_ext, s->volumes[v].max_density);
+        s->root_min_ext = fminf(s->root_min_ext, s->volumes[v].min_density);
+    }
+    for (int a = 0; a < 3; ++a) { rmin[a] -= 1.0f; rmax[a] += 1.0f; }               /* bvh_builder.cpp:77-78 */
+    s->leaf_lists = calloc(512 * 601, sizeof(int));
+    memset(s->node_exists, 0, sizeof(s->node_exists)); memset(s->node_nvol, 0, sizeof(s->node_nvol));
+    memcpy(s->node_min[0], rmin, 12); memcpy(s->node_max[0], rmax, 12); s->node_exists[0] = 1; s->node_nvol[0] = s->n_volumes;
+    for (int j = 1; j < 585; ++j) {
+        int parent, c;
+        if (j < 9) { parent = 0; c = j - 1; }
+        else if (j < 73) { parent = 1 + ((j - 9) >> 3); c = (j - 9) & 7; }
+        else { parent = 9 + ((j - 73) >> 3); c = (j - 73) & 7; }
+        if (!s->node_exists[parent] || s->node_nvol[parent] == 0) continue;     /* children only under non-empty nodes */
+        s->node_exists[j] = 1;
+        child_box(c, s->node_min[parent], s->node_max[parent], s->node_min[j], s->node_max[j]);
+        int cnt = 0;
+        for (int v = 0; v < s->n_volumes; ++v) {                                    /* Overlaps, AABB.h:135-140 */
+            int ov = 1;
+            for (int a = 0; a < 3; ++a) ov &= (s->node_max[j][a] >= blo[v][a]) && (s->node_min[j][a] <= bhi[v][a]);
+            if (ov) { if (j >= 73) s->leaf_lists[(j - 73) * 601 + 1 + cnt] = v; cnt++; }
+        }
+        s->node_nvol[j] = cnt;
+        if (j >= 73) s->leaf_lists[(j - 73) * 601] = cnt;
+    }
+    free(blo); free(bhi);
+    return 0;
+}
+
+void orc_release(orc_scene* s) { free(s->leaf_lists); s->leaf_lists = NULL; }
+
+/* ---- texture sampling: CUDA linear filtering (normalised coords, 8-bit weights) ------------------ */
+static inline float q8(float f) { return floorf(f * 256.0f + 0.5f) * (1.0f / 256.0f); }
+static float tex3d1(const float* d, const int dim[3], float u, float v, float w) {
+    float x = u * dim[0] - 0.5f, y = v * dim[1] - 0.5f, z = w * dim[2] - 0.5f;
+    float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    float a = q8(x - fx), b = q8(y - fy), c = q8(z - fz);
+    int i0 = (int)fx, j0 = (int)fy, k0 = (int)fz, i1 = i0 + 1, j1 = j0 + 1, k1 = k0 + 1;
+#define CL(i, n) ((i) < 0 ? 0 : ((i) >= (n) ? (n) - 1 : (i)))
+    i0 = CL(i0, dim[0]); i1 = CL(i1, dim[0]); j0 = CL(j0, dim[1]); j1 = CL(j1, dim[1]); k0 = CL(k0, dim[2]); k1 = CL(k1, dim[2]);
+#define T(i, j, k) d[((size_t)(k) * dim[1] + (j)) * dim[0] + (i)]
+    return (1 - a) * (1 - b) * (1 - c) * T(i0, j0, k0) + a * (1 - b) * (1 - c) * T(i1, j0, k0) + (1 - a) * b * (1 - c) * T(i0, j1, k0) + a * b * (1 - c) * T(i1, j1, k0)
+         + (1 - a) * (1 - b) * c * T(i0, j0, k1) + a * (1 - b) * c * T(i1, j0, k1) + (1 - a) * b * c * T(i0, j1, k1) + a * b * c * T(i1, j1, k1);
+#undef T
+}
+static v3 tex3d4(const float* d, const int dim[3], float u, float v, float w) {
+    float x = u * dim[0] - 0.5f, y = v * dim[1] - 0.5f, z = w * dim[2] - 0.5f;
+    float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    float a = q8(x - fx), b = q8(y - fy), c = q8(z - fz);
+    int i0 = (int)fx, j0 = (int)fy, k0 = (int)fz, i1 = i0 + 1, j1 = j0 + 1, k1 = k0 + 1;
+    i0 = CL(i0, dim[0]); i1 = CL(i1, dim[0]); j0 = CL(j0, dim[1]); j1 = CL(j1, dim[1]); k0 = CL(k0, dim[2]); k1 = CL(k1, dim[2]);
+    float r[3];
+    for (int ch = 0; ch < 3; ++ch) {
+#define T4(i, j, k) d[(((size_t)(k) * dim[1] + (j)) * dim[0] + (i)) * 4 + ch]
+        r[ch] = (1 - a) * (1 - b) * (1 - c) * T4(i0, j0, k0) + a * (1 - b) * (1 - c) * T4(i1, j0, k0) + (1 - a) * b * (1 - c) * T4(i0, j1, k0) + a * b * (1 - c) * T4(i1, j1, k0)
+              + (1 - a) * (1 - b) * c * T4(i0, j0, k1) + a * (1 - b) * c * T4(i1, j0, k1) + (1 - a) * b * c * T4(i0, j1, k1) + a * b * c * T4(i1, j1, k1);
+#undef T4
+    }
+    return V(r[0], r[1], r[2]);
+}
+static v3 tex2d_env(const orc_scene* s, float u, float v) {                          /* wrap in u, clamp in v (main.cpp:967-972) */
+    float x = u * s->env_w - 0.5f, y = v * s->env_h - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float a = q8(x - fx), b = q8(y - fy);
+    int i0 = (int)fx, j0 = (int)fy, i1 = i0 + 1, j1 = j0 + 1;
+    i0 = ((i0 % s->env_w) + s->env_w) % s->env_w; i1 = ((i1 % s->env_w) + s->env_w) % s->env_w;
+    j0 = CL(j0, s->env_h); j1 = CL(j1, s->env_h);
+    float r[3];
+    for (int ch = 0; ch < 3; ++ch) {
+#define E(i, j) s->env_rgba[((size_t)(j) * s->env_w + (i)) * 4 + ch]
+        r[ch] = (1 - a) * (1 - b) * E(i0, j0) + a * (1 - b) * E(i1, j0) + (1 - a) * b * E(i0, j1) + a * b * E(i1, j1);
+#undef E
+    }
+    return V(r[0], r[1], r[2]);
+}
+
+/* ---- geometry ------------------------------------------------------------------------------------- */
+static int box_intersect(const float pmin[3], const float pmax[3], v3 o, v3 d, float* tmin, float* tmax) {   /* AABB.h:182-205 */
+    float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+    float t1 = (pmin[0] - o.x) * ix, t2 = (pmax[0] - o.x) * ix, t3 = (pmin[1] - o.y) * iy, t4 = (pmax[1] - o.y) * iy;
+    float t5 = (pmin[2] - o.z) * iz, t6 = (pmax[2] - o.z) * iz;
+    *tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+    *tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+    if (*tmax <= 0.0f) return 0;
+    if (*tmin > *tmax) return 0;
+    if (*tmin < 0) { *tmin = *tmax; if (*tmin < 0) return 0; }
+    return 1;
+}
+static int box_contains(const float pmin[3], const float pmax[3], v3 p) {
+    return p.x >= pmin[0] && p.x <= pmax[0] && p.y >= pmin[1] && p.y <= pmax[1] && p.z >= pmin[2] && p.z <= pmax[2];
+}
+static int find_discr(float a, float b, float c, float* x1, float* x2) {             /* geometry.h:46-70 */
+    if (b == 0) { if (a == 0) return 0; *x1 = 0; *x2 = sqrtf(-c / a); return 1; }
+    float discr = b * b - 4 * a * c;
+    if (discr < 0) return 0;
+    float q = (b < 0.f) ? -0.5f * (b - sqrtf(discr)) : -0.5f * (b + sqrtf(discr));
+    *x1 = q / a; *x2 = c / q;
+    return 1;
+}
+static int sphere_intersect(const orc_scene* s, v3 p, v3 d, float* t_min, float* t_max) {   /* geometry.h:114-137 */
+    v3 o = sub(p, V(s->sph_center[0], s->sph_center[1], s->sph_center[2]));
+    float A = dot(d, d), B = 2 * dot(d, o), C = dot(o, o) - s->sph_radius * s->sph_radius;
+    if (!find_discr(A, B, C, t_min, t_max)) return 0;
+    if (*t_min > *t_max) { float t = *t_max; *t_max = *t_min; *t_min = t; }
+    if (*t_min < 0) { *t_min = *t_max; if (*t_min < 0) return 0; }
+    return 1;
+}
+static int closest_object(const orc_scene* s, v3 p, v3 d, float* t_min) {            /* render_kernel.cu:1118-1135 */
+    float tmin1 = M_INF_F, tmax1 = -M_INF_F, tmin2 = M_INF_F, tmax2 = -M_INF_F;
+    int i1 = box_intersect(s->node_min[0], s->node_max[0], p, d, &tmin1, &tmax1);
+    int i2 = sphere_intersect(s, p, d, &tmin2, &tmax2);
+    if (i1 && !i2) { *t_min = tmin1; return 1; }
+    if (!i1 && i2) { *t_min = tmin2; return 2; }
+    if (i1 && i2) { if (tmin1 < tmin2) { *t_min = tmin1; return 1; } if (tmin2 < tmin1) { *t_min = tmin2; return 2; } }
+    return 0;
+}
+static int get_quadrant(const orc_scene* s, int node, int first_child, v3 p) {       /* render_kernel.cu:1102-1115 */
+    (void)node;
+    for (int i = 0; i < 8; ++i) if (s->node_exists[first_child + i] && box_contains(s->node_min[first_child + i], s->node_max[first_child + i], p)) return i;
+    return -1;
+}
+/* octree point location with empty-space skipping shared by sample / Tr / estimate_emission.
+ * returns leaf 0..511, -1 = left the tree (break), -2 = skipped an empty node (continue) */
+static int locate_or_skip(const orc_scene* s, v3* p, v3 d) {
+    float t_min, t_max;
+    int c1 = get_quadrant(s, 0, 1, *p); if (c1 < 0) return -1;
+    int n1 = 1 + c1;
+    if (s->node_nvol[n1] == 0) { box_intersect(s->node_min[n1], s->node_max[n1], *p, d, &t_min, &t_max); t_max = fmaxf(t_max, 0.1f); *p = add(*p, scl(d, t_max)); return -2; }
+    int c2 = get_quadrant(s, n1, 9 + c1 * 8, *p); if (c2 < 0) return -1;
+    int n2 = 9 + c1 * 8 + c2;
+    if (s->node_nvol[n2] == 0) { box_intersect(s->node_min[n2], s->node_max[n2], *p, d, &t_min, &t_max); t_max = fmaxf(t_max, 0.1f); *p = add(*p, scl(d, t_max)); return -2; }
+    int c3 = get_quadrant(s, n2, 73 + c1 * 64 + c2 * 8, *p); if (c3 < 0) return -1;
+    int n3 = 73 + c1 * 64 + c2 * 8 + c3;
+    if (s->node_nvol[n3] == 0) { box_intersect(s->node_min[n3], s->node_max[n3], *p, d, &t_min, &t_max); t_max = fmaxf(t_max, 0.1f); *p = add(*p, scl(d, t_max)); return -2; }
+    return n3 - 73;
+}
+
+/* ---- volume lookups (render_kernel.cu:909-1014) ----------------------------------------------------- */
+static int vol_coord(const orc_volume* g, v3 p, float uvw[3]) {
+    for (int r = 0; r < 3; ++r) {
+        const float* m = g->inv + 4 * r;
+        float q = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3];
+        q -= g->bmin[r]; q /= (float)g->dim[r];
+        uvw[r] = q;
+    }
+    return !(uvw[0] < 0 || uvw[1] < 0 || uvw[2] < 0 || uvw[0] > 1 || uvw[1] > 1 || uvw[2] > 1);
+}
+static float sum_density(const orc_scene* s, int leaf, v3 p) {
+    const int* l = s->leaf_lists + leaf * 601; float d = 0.0f;
+    for (int i = 0; i < l[0]; ++i) { const orc_volume* g = &s->volumes[l[1 + i]]; float uvw[3]; if (vol_coord(g, p, uvw)) d += tex3d1(g->density, g->dim, uvw[0], uvw[1], uvw[2]); }
+    return d;
+}
+static v3 sum_color(const orc_scene* s, int leaf, v3 p) {
+    const int* l = s->leaf_lists + leaf * 601; v3 c = V(0, 0, 0);
+    for (int i = 0; i < l[0]; ++i) {
+        const orc_volume* g = &s->volumes[l[1 + i]]; v3 cc = V(1, 1, 1); float uvw[3];
+        if (g->color4) cc = vol_coord(g, p, uvw) ? tex3d4(g->color4, g->cdim, uvw[0], uvw[1], uvw[2]) : V(0, 0, 0);
+        c = V(fmaxf(c.x, cc.x), fmaxf(c.y, cc.y), fmaxf(c.z, cc.z));
+    }
+    return c;
+}
+static v3 sum_emission(const orc_scene* s, const vpt_kernel_params* kp, int leaf, v3 p) {
+    const int* l = s->leaf_lists + leaf * 601; v3 e = V(0, 0, 0);
+    for (int i = 0; i < l[0]; ++i) {
+        const orc_volume* g = &s->volumes[l[1 + i]]; float uvw[3];
+        if (!g->emission || !vol_coord(g, p, uvw)) continue;
+        float index = tex3d1(g->emission, g->edim, uvw[0], uvw[1], uvw[2]);
+        index = clampf(index * 255.0f / kp->emission_pivot, 0.f, 255.0f);
+        const float* L = s->emission_lut + 3 * (int)index;
+        e = add(e, scl(V(L[0], L[1], L[2]), kp->emission_scale));
+    }
+    return e;
+}
+
+/* ---- phase function, sun direction ------------------------------------------------------------------ */
+static float henyey_greenstein(float cos_theta, float g) {                          /* light.h:55-64, pi/4 scale (Q1) */
+    float den = 1 + g * g - 2 * g * cos_theta;
+    return 0.785398163397448309616f * (1 - g * g) / (den * sqrtf(den));
+}
+static void sample_hg(v3* wo, rng_t* r, float g) {                                   /* render_kernel.cu:306-325 */
+    float cos_theta;
+    if (fabsf(g) < EPS) cos_theta = 1 - 2 * rnd(r);
+    else { float sq = (1 - g * g) / (1 - g + 2 * g * rnd(r)); cos_theta = (1 + g * g - sq * sq) / (2 * g); }
+    float sin_theta = sqrtf(fmaxf(0.f, 1.0f - cos_theta * cos_theta));
+    float phi = 6.2831855f * rnd(r);
+    v3 v1 = scl(*wo, -1.0f), v2, v3_;
+    if (fabsf(v1.x) > fabsf(v1.y)) v2 = V(-v1.z, 0.0f, v1.x); else v2 = V(0.0f, v1.z, -v1.y);
+    v2 = nrm(v2); v3_ = nrm(crs(v1, v2));
+    *wo = add(add(scl(scl(v2, sin_theta), cosf(phi)), scl(scl(v3_, sin_theta), sinf(phi))), scl(*wo, cos_theta));
+}
+static v3 degree_to_cartesian(float azimuth, float elevation) {                     /* render_kernel.cu:126-142 */
+    float az = clampf(azimuth, 0.f, 360.0f), el = clampf(elevation, -90.0f, 90.0f);
+    az = az * PI_F / 180.0f; el = (90.0f - el) * PI_F / 180.0f;
+    return nrm(V(sinf(el) * cosf(az), cosf(el), sinf(el) * sinf(az)));
+}
+
+/* ---- residual ratio tracking (render_kernel.cu:1138-1273) ------------------------------------------- */
+static v3 Tr(rng_t* r, v3 p, v3 d, const vpt_kernel_params* kp, const orc_scene* s) {
+    float tr = 1.0f, t_min, t_max, geo_dist = 0.f, distance = 0.f, t = 0.0f;
+    if (!box_contains(s->node_min[0], s->node_max[0], p)) {
+        if (box_intersect(s->node_min[0], s->node_max[0], p, d, &t_min, &t_max)) p = add(p, scl(d, t_min + EPS));
+        else return V(1, 1, 1);
+    }
+    box_intersect(s->node_min[0], s->node_max[0], p, d, &t_min, &distance);
+    if (sphere_intersect(s, p, d, &geo_dist, &t_max)) return V(0, 0, 0);
+    float sigma_c = s->root_min_ext, sigma_r_inv = 1.0f / (s->root_max_ext - sigma_c), T_c = expf(-sigma_c * distance);
+    for (;;) {
+        int leaf = locate_or_skip(s, &p, d);
+        if (leaf == -2) continue;
+        if (leaf < 0) break;
+        t -= logf(1 - rnd(r)) * sigma_r_inv * kp->tr_depth;
+        if (t >= distance) break;
+        p = add(p, scl(d, t));
+        if (!box_contains(s->node_min[0], s->node_max[0], p)) break;
+        float density = sum_density(s, leaf, p);
+        tr *= 1 - ((density - sigma_c) * sigma_r_inv);
+        if (len(V(tr, tr, tr)) < EPS) break;
+    }
+    float c = clampf(tr * T_c, 0.f, 1.0f);
+    return V(c, c, c);
+}
+
+static v3 estimate_emission(rng_t* r, v3 p, v3 d, const vpt_kernel_params* kp, const orc_scene* s) {   /* :1275-1339 */
+    if (kp->emission_scale == 0) return V(0, 0, 0);
+    v3 e = V(0, 0, 0); float t = 0.0f;
+    for (;;) {
+        int leaf = locate_or_skip(s, &p, d);
+        if (leaf == -2) continue;
+        if (leaf < 0) break;
+        float inv_max_density = 1 / s->root_max_ext;
+        t -= logf(1 - rnd(r)) * inv_max_density * kp->tr_depth / kp->extinction.x;
+        p = add(p, scl(d, t));
+        if (!box_contains(s->node_min[0], s->node_max[0], p)) break;
+        e = add(e, sum_emission(s, kp, leaf, p));
+    }
+    return e;
+}
+
+/* ---- delta tracking (render_kernel.cu:1556-1681, DDA_STEP_TRUE branch) ------------------------------- */
+static v3 sample_walk(rng_t* r, v3* p, v3 d, int* interaction, int* obj, float* Alpha, const vpt_kernel_params* kp, const orc_scene* s) {
+    float t_min, t_max, geo_dist = 0.f, distance = 0.f, t = 0.0f;
+    for (;;) {
+        int leaf = locate_or_skip(s, p, d);
+        if (leaf == -2) continue;
+        if (leaf < 0) break;
+        float inv_max_density = 1.0f / s->root_max_ext, inv_density_mult = 1.0f / kp->density_mult;
+        box_intersect(s->node_min[0], s->node_max[0], *p, d, &t_min, &distance);
+        if (sphere_intersect(s, *p, d, &geo_dist, &t_max)) distance = geo_dist;
+        t -= logf(1 - rnd(r)) * inv_max_density * inv_density_mult;
+        if (t >= distance) { *obj = 2; break; }                 /* compiled reference: obj = 2 on every distance exit (uninitialised `geo`, Q4) */
+        *p = add(*p, scl(d, t));
+        if (!box_contains(s->node_min[0], s->node_max[0], *p)) break;
+        float density = sum_density(s, leaf, *p);
+        v3 Cd = sum_color(s, leaf, *p);
+        int index = (int)floorf(fminf(fmaxf(density * inv_max_density * 255.0f / kp->emission_pivot, 0.0f), 255.0f));
+        const float* dc = s->density_color_lut + 3 * index;
+        if (*Alpha < 1.0f) *Alpha += density;
+        if (density * inv_max_density > rnd(r)) {
+            *interaction = 1;
+            return scl(divv(mul(mul(from3(kp->albedo), Cd), V(dc[0], dc[1], dc[2])), from3(kp->extinction)), (float)kp->energy_inject);
+        }
+    }
+    return V(1, 1, 1);
+}
+
+static v3 estimate_sun(const vpt_kernel_params* kp, rng_t* r, v3 p, v3 dir, const orc_scene* s) {      /* :1478-1516 */
+    v3 wi = degree_to_cartesian(kp->azimuth, kp->elevation);
+    float phase_pdf = henyey_greenstein(dot(dir, wi), kp->phase_g1);
+    v3 tr = Tr(r, p, wi, kp, s);
+    return scl(mul(scl(tr, phase_pdf), from3(kp->sun_color)), kp->sun_mult);
+}
+
+static v3 estimate_point_light(const vpt_kernel_params* kp, rng_t* r, v3 p, v3 dir, const orc_scene* s) {   /* :1445-1475, light.h:104-121 */
+    v3 Ld = V(0, 0, 0); int budget = 10;
+    while (budget >= 0) {
+        int li = (int)floorf(rnd(r) * (float)s->n_lights);
+        const float* L = s->lights + 7 * li; v3 lpos = V(L[0], L[1], L[2]);
+        v3 tr = Tr(r, p, nrm(sub(lpos, p)), kp, s);
+        if (budget < s->n_lights) {
+            v3 wi = nrm(sub(lpos, p));
+            float phase_pdf = henyey_greenstein(dot(dir, wi), kp->phase_g1);
+            float sqr_dist = len(sub(mul(lpos, lpos), mul(p, p)));               /* quirk Q9 */
+            Ld = add(Ld, scl(scl(mul(scl(V(L[3], L[4], L[5]), L[6]), tr), phase_pdf), 1 / sqr_dist));
+        }
+        budget--;
+    }
+    return Ld;
+}
+
+/* ---- direct integrator (render_kernel.cu:1760-1857), HDRI environment branch ------------------------- */
+static v3 direct_integrator(rng_t rs, v3 p, v3 d, float* tr, const vpt_kernel_params* kp, const orc_scene* s) {
+    v3 L = V(0, 0, 0), beta = V(1, 1, 1), env_pos = p; int mi = 0, obj; float t_min;
+    v3 sphc = V(s->sph_center[0], s->sph_center[1], s->sph_center[2]);
+    for (int rd = 1; rd <= kp->ray_depth; rd++) {
+        obj = closest_object(s, p, d, &t_min);
+        if (obj == 0) break;                                     /* identical no-op iterations follow */
+        if (obj == 1) {
+            p = add(p, scl(d, t_min + EPS));
+            for (int vd = 1; vd <= kp->volume_depth; vd++) {
+                mi = 0;
+                beta = mul(beta, sample_walk(&rs, &p, d, &mi, &obj, tr, kp, s));
+                if (is_black(beta) || obj == 2) break;
+                if (mi) sample_hg(&d, &rs, kp->phase_g1);
+            }
+            if (mi) {
+                L = add(L, mul(estimate_sun(kp, &rs, p, d, s), beta));
+                if (s->n_lights > 0) L = add(L, mul(estimate_point_light(kp, &rs, p, d, s), beta));
+            }
+            if (kp->emission_scale > 0 && mi) L = add(L, estimate_emission(&rs, p, d, kp, s));
+        }
+        obj = closest_object(s, p, d, &t_min);
+        if (obj == 2) {
+            p = add(p, scl(d, t_min));
+            v3 normal = nrm(scl(sub(p, sphc), 1.0f / s->sph_radius));
+            v3 nl = dot(normal, d) < 0 ? normal : scl(normal, -1);
+            float phi = 2 * PI_F * rnd(&rs), r2 = rnd(&rs), r2s = sqrtf(r2);
+            v3 w = nrm(nl), u = nrm(crs(fabs(w.x) > .1 ? V(0, 1, 0) : V(1, 0, 0), w)), v = crs(w, u);
+            v3 hemi = nrm(add(add(scl(scl(u, cosf(phi)), r2s), scl(scl(v, sinf(phi)), r2s)), scl(w, sqrtf(1 - r2))));
+            v3 refl = sub(d, scl(nl, 2.0f * dot(nl, d)));
+            d = lerp3(refl, hemi, s->sph_roughness);
+            v3 light_dir = degree_to_cartesian(kp->azimuth, kp->elevation);
+            p = add(p, scl(normal, EPS));
+            beta = mul(beta, V(s->sph_color[0], s->sph_color[1], s->sph_color[2]));
+            v3 v_tr = Tr(&rs, p, light_dir, kp, s);
+            L = add(L, mul(scl(mul(scl(from3(kp->sun_color), kp->sun_mult), v_tr), fmaxf(dot(light_dir, normal), 0.f)), beta));
+            env_pos = p;
+        }
+    }
+    (void)env_pos;
+    if (kp->environment_type != 0) {
+        v3 e = tex2d_env(s, atan2f(d.z, d.x) * (float)(0.5 / 3.14159265358979323846) + 0.5f, acosf(fmaxf(fminf(d.y, 1.0f), -1.0f)) * (float)(1.0 / 3.14159265358979323846));
+        L = add(L, scl(mul(mul(e, from3(kp->sky_color)), beta), 1.0f / (4.0f * PI_F)));
+    }
+    *tr = fminf(*tr, 1.0f);
+    return L;
+}
+
+static float depth_calculator(rng_t rs, v3 p, v3 d, float* tr, const vpt_kernel_params* kp, const orc_scene* s) {   /* :1859-1889 */
+    v3 orig = p; int mi = 0, obj; float t_min;
+    obj = closest_object(s, p, d, &t_min);
+    if (obj == 1) { p = add(p, scl(d, t_min + EPS)); sample_walk(&rs, &p, d, &mi, &obj, tr, kp, s); return mi ? len(sub(orig, p)) : 0.f; }
+    if (obj == 2) { p = add(p, scl(d, t_min)); return len(sub(orig, p)); }
+    return 0.f;
+}
+
+static float van_der_corput(rng_t* r, int base) {                                    /* camera.h:49-62 */
+    int n = (int)(rnd(r) * 100); float rand_int = 0, denom = 1, invBase = 1.f / base;
+    while (n) { denom *= base; rand_int += (n % base) / denom; n = (int)(n * invBase); }
+    return rand_int;
+}
+
+static v3 aces_fit(v3 v) {
+    v3 a = sub(mul(v, add(v, V(0.0245786f, 0.0245786f, 0.0245786f))), V(0.000090537f, 0.000090537f, 0.000090537f));
+    v3 b = add(mul(v, add(scl(v, 0.983729f), V(0.4329510f, 0.4329510f, 0.4329510f))), V(0.238081f, 0.238081f, 0.238081f));
+    return divv(a, b);
+}
+
+/* One progressive pass over the pixel rectangle [x0,x1) x [y0,y1) (volume_rt_kernel, :2216-2326, with the
+ * blue-noise update done after all pixels = the race-free protocol).  Buffers are full-frame, row-major. */
+int orc_render_pass(const orc_scene* s, const vpt_camera* cam, const vpt_kernel_params* kp, int x0, int y0, int x1, int y1,
+                    float* accum, float* depth_buf, float* raw4, uint32_t* display, const float* blue_noise)
+{
+    const int W = (int)kp->resolution.x, H = (int)kp->resolution.y;
+    if (kp->integrator != 0 || kp->environment_type == 0) return -3;
+    if (x1 > W) x1 = W; if (y1 > H) y1 = H;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = y0; y < y1; ++y) for (int x = x0; x < x1; ++x) {
+        const uint32_t idx = (uint32_t)y * (uint32_t)W + (uint32_t)x;
+        rng_t rs; rng_init(&rs, idx, kp->iteration);
+        const float* bn = blue_noise + 3 * ((y % 256) * 256 + (x % 256));
+        float u = (float)(x + bn[0]) / (float)W, v = (float)(y + bn[1]) / (float)H;
+        v3 pd;
+        do { float a = van_der_corput(&rs, 2), b = van_der_corput(&rs, 3); pd = V(2.0f * a - 1.0f, 2.0f * b - 1.0f, 0.f); } while (dot(pd, pd) >= 1.0);
+        v3 rdl = scl(pd, cam->lens_radius);
+        v3 offset = add(scl(from3(cam->u), rdl.x), scl(from3(cam->v), rdl.y));
+        (void)rnd(&rs);
+        v3 org = add(from3(cam->origin), offset);
+        v3 dir = nrm(sub(sub(add(add(from3(cam->lower_left_corner), scl(from3(cam->horizontal), u)), scl(from3(cam->vertical), v)), from3(cam->origin)), offset));
+        v3 value = V(1, 1, 1); float depth = 0.f, tr = 0.f;
+        if (kp->iteration < kp->max_interactions && kp->render) {
+            depth = depth_calculator(rs, org, dir, &tr, kp, s);
+            value = direct_integrator(rs, org, dir, &tr, kp, s);
+        }
+        float* A = accum + 3 * (size_t)idx;
+        if (isnan(value.x) || isnan(value.y) || isnan(value.z) || isinf(value.x) || isinf(value.y) || isinf(value.z)) value = V(A[0], A[1], A[2]);
+        if (isnan(tr) || isinf(tr)) tr = 1.0f;
+        if (kp->iteration == 0) { A[0] = value.x; A[1] = value.y; A[2] = value.z; if (depth_buf) depth_buf[idx] = depth; }
+        else if (kp->iteration < kp->max_interactions) {
+            float n = (float)(kp->iteration + 1);
+            A[0] += (value.x - A[0]) / n; A[1] += (value.y - A[1]) / n; A[2] += (value.z - A[2]) / n;
+            if (depth_buf) depth_buf[idx] += (depth - depth_buf[idx]) / n;
+        }
+        if (raw4 || display) {
+            v3 a = V(A[0], A[1], A[2]);
+            v3 val = V(0.59719f * a.x + 0.35458f * a.y + 0.04823f * a.z, 0.07600f * a.x + 0.90834f * a.y + 0.01566f * a.z, 0.02840f * a.x + 0.13383f * a.y + 0.83777f * a.z);
+            val = aces_fit(val);
+            val = scl(V(1.60475f * val.x - 0.53108f * val.y - 0.07367f * val.z, -0.10208f * val.x + 1.10813f * val.y - 0.00605f * val.z, -0.00327f * val.x - 0.07276f * val.y + 1.07602f * val.z), kp->exposure_scale);
+            if (display) {
+                unsigned r = (unsigned)(255.0f * fminf(powf(fmaxf(val.x, 0.0f), (float)(1.0 / 2.2)), 1.0f));
+                unsigned g = (unsigned)(255.0f * fminf(powf(fmaxf(val.y, 0.0f), (float)(1.0 / 2.2)), 1.0f));
+                unsigned b = (unsigned)(255.0f * fminf(powf(fmaxf(val.z, 0.0f), (float)(1.0 / 2.2)), 1.0f));
+                display[idx] = 0xff000000u | (r << 16) | (g << 8) | b;
+            }
+            if (raw4) { raw4[4 * (size_t)idx] = val.x; raw4[4 * (size_t)idx + 1] = val.y; raw4[4 * (size_t)idx + 2] = val.z; raw4[4 * (size_t)idx + 3] = tr; }
+        }
+    }
+    return 0;
+}
+
+void orc_bn_advance(float* bn) {                                                    /* render_kernel.cu:2319-2325 */
+    const float g = (1.0f + sqrtf(5.0f)) / 2.0f;
+    for (int i = 0; i < 256 * 256 * 3; ++i) bn[i] = fmodf(bn[i] + g, 1.0f);
+}
+
+size_t orc_sizeof_scene(void) { return sizeof(orc_scene); }
+size_t orc_sizeof_volume(void) { return sizeof(orc_volume); }

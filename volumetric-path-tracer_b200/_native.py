@@ -150,7 +150,7 @@ EXPORTED_SYMBOLS = [
     "vpt_local_pixels", "vpt_unpermute", "vpt_render_pass", "vpt_render_passes", "vpt_invalidate_scene", "vpt_get_stats",
     "vpt_texture_create_3d", "vpt_texture_create_env", "vpt_texture_destroy", "vpt_vdb_load", "vpt_hdr_load",
     "vpt_bmp_load_rbg", "vpt_exr_load_rgb", "vpt_free", "vpt_octree_build", "vpt_octree_destroy", "vpt_volume_bounds",
-    "vpt_camera_look_at", "vpt_kernel_params_defaults",
+    "vpt_camera_look_at", "vpt_kernel_params_defaults", "vpt_get_counters", "vpt_get_kernel_times", "vpt_octree_read",
 ]
 
 # ---- prototypes ------------------------------------------------------------------------------------
@@ -168,6 +168,8 @@ lib.vpt_render_pass.argtypes = [_vp, C.POINTER(_vp), _vp]; lib.vpt_render_pass.r
 lib.vpt_render_passes.argtypes = [_vp, C.POINTER(_vp), C.c_uint, _vp]; lib.vpt_render_passes.restype = C.c_int
 lib.vpt_invalidate_scene.argtypes = [_vp]; lib.vpt_invalidate_scene.restype = C.c_int
 lib.vpt_get_stats.argtypes = [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint)]; lib.vpt_get_stats.restype = C.c_int
+lib.vpt_get_counters.argtypes = [_vp, C.POINTER(C.c_ulonglong), C.c_int]; lib.vpt_get_counters.restype = C.c_int
+lib.vpt_get_kernel_times.argtypes = [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]; lib.vpt_get_kernel_times.restype = C.c_int
 lib.vpt_texture_create_3d.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(_vp)]
 lib.vpt_texture_create_3d.restype = C.c_int
 lib.vpt_texture_create_env.argtypes = [C.POINTER(C.c_float), C.c_uint, C.c_uint, C.POINTER(C.c_uint64), C.POINTER(_vp)]
@@ -181,6 +183,7 @@ lib.vpt_exr_load_rgb.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.
 lib.vpt_free.argtypes = [_vp]; lib.vpt_free.restype = None
 lib.vpt_octree_build.argtypes = [C.POINTER(GPU_VDB), C.c_int, C.POINTER(C.c_uint64)]; lib.vpt_octree_build.restype = C.c_int
 lib.vpt_octree_destroy.argtypes = [C.c_uint64]; lib.vpt_octree_destroy.restype = C.c_int
+lib.vpt_octree_read.argtypes = [C.c_uint64, C.POINTER(OCTNode), C.POINTER(C.c_int)]; lib.vpt_octree_read.restype = C.c_int
 lib.vpt_volume_bounds.argtypes = [C.POINTER(GPU_VDB), C.POINTER(C.c_float)]; lib.vpt_volume_bounds.restype = None
 lib.vpt_camera_look_at.argtypes = [C.POINTER(camera), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float]
 lib.vpt_camera_look_at.restype = None

@@ -300,6 +300,7 @@ struct PathState {
     bool   mi, first_walk, geo;
     int    obj;
     uint32_t lp, pass;
+    uint32_t nlook;       // density / emission lookups issued by this lane (statistics)
     Rng    rng;
 };
 
@@ -335,6 +336,7 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
     st.wpos += st.wdir * st.t;                                // cumulative t, never reset (quirk Q2)
     if (!aabb_contains(sc.root_pmin, sc.root_pmax, st.wpos)) { st.mode = W_NONE; st.exit_reason = EX_OUTSIDE; return; }
 
+    st.nlook++;
     if (st.mode == W_EMIT) {
         st.emis += leaf_emission(sc, leaf, st.wpos, reinterpret_cast<const float3*>(kp.emission_texture), kp.emission_pivot, kp.emission_scale);
         return;
@@ -566,8 +568,9 @@ k_trace(const FrameArgs fa)
 
     const unsigned q_count = *fa.queue_count;
     PathState st;
-    st.phase = PH_IDLE; st.mode = W_NONE;
+    st.phase = PH_IDLE; st.mode = W_NONE; st.nlook = 0;
     bool queue_dry = false;
+    uint32_t lane_steps = 0, warp_iters = 0, lane_trans = 0, warp_trans = 0;
 
     for (;;) {
         // ---- refill idle lanes from the ray queue (one atomic per warp) ----
@@ -599,7 +602,8 @@ k_trace(const FrameArgs fa)
         if (__ballot_sync(0xffffffffu, st.phase != PH_IDLE) == 0u) break;
 
         // ---- estimator transitions for every lane that is between walks ----
-        if (st.phase != PH_IDLE && st.mode == W_NONE) transition(st, fs, fa, tc, sph);
+        if (st.phase != PH_IDLE && st.mode == W_NONE) { transition(st, fs, fa, tc, sph); lane_trans++; }
+        warp_trans++;
 
         // ---- converged step loop: keep stepping while enough lanes are inside a walk ----
         for (;;) {
@@ -607,7 +611,19 @@ k_trace(const FrameArgs fa)
             if (walking == 0u) break;
             const unsigned waiting = __ballot_sync(0xffffffffu, st.mode == W_NONE && (st.phase != PH_IDLE || !queue_dry));
             if (waiting != 0u && __popc(walking) < kServiceThreshold) break;
-            if (st.mode != W_NONE) walk_step(st, fs, fa, tc, sph);
+            if (st.mode != W_NONE) { walk_step(st, fs, fa, tc, sph); lane_steps++; }
+            warp_iters++;
+        }
+    }
+
+    if (fa.counters) {                                        // optional statistics (one atomic set per warp)
+        unsigned long long a = st.nlook, b = lane_steps, c = lane_trans;
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        if (lane == 0) {
+            atomicAdd(fa.counters + 0, a); atomicAdd(fa.counters + 1, b); atomicAdd(fa.counters + 2, (unsigned long long)warp_iters);
+            atomicAdd(fa.counters + 3, c); atomicAdd(fa.counters + 4, (unsigned long long)warp_trans);
         }
     }
 }

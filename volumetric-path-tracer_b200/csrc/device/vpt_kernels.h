@@ -32,6 +32,8 @@ struct FrameArgs {
     unsigned* queue_head;
     // sample planes, [pass][local pixel]
     float4 *planeA, *planeB, *planeC, *planeD;   // planeD (env_pos) only for environment_type == 0, else null
+    // optional statistics: [0] volume lookups, [1] lane-steps, [2] warp step iterations, [3] lane transitions, [4] warp transition rounds
+    unsigned long long* counters;
 };
 
 cudaError_t launch_prepare_scene(const vpt_gpu_vdb* vols, const vpt_octnode* root, SceneTables* out, OctInternal* internal,

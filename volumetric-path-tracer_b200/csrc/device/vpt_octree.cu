@@ -140,6 +140,43 @@ cudaError_t octree_build_device(vpt_octnode* d_nodes, const vpt_gpu_vdb* d_vols,
     return e != cudaSuccess ? e : e2;
 }
 
+// Copy a pointer-linked octree (either builder's, including device-heap nodes that cudaMemcpy cannot read)
+// into a flat 585-entry array in the canonical numbering; exists[j] = 0 for nodes that were never allocated.
+__global__ void k_octree_snapshot(const vpt_octnode* root, vpt_octnode* out, int* exists)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= kOctNodes) return;
+    int level, c[3] = {0, 0, 0};
+    if (j == 0) level = 0;
+    else if (j < 9) { level = 1; c[0] = j - 1; }
+    else if (j < 73) { level = 2; c[0] = (j - 9) >> 3; c[1] = (j - 9) & 7; }
+    else { level = 3; c[0] = (j - 73) >> 6; c[1] = ((j - 73) >> 3) & 7; c[2] = (j - 73) & 7; }
+    const vpt_octnode* n = root;
+    bool ok = true;
+    for (int l = 0; l < level; ++l) {
+        if (n->num_volumes <= 0) { ok = false; break; }
+        n = reinterpret_cast<const vpt_octnode*>((uintptr_t)n->children[c[l]]);
+    }
+    exists[j] = ok ? 1 : 0;
+    if (ok) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(n); uint32_t* dst = reinterpret_cast<uint32_t*>(&out[j]);
+        for (int w = 0; w < (int)(sizeof(vpt_octnode) / 4); ++w) dst[w] = src[w];
+    }
+}
+
+cudaError_t octree_snapshot(const vpt_octnode* d_root, vpt_octnode* h_nodes, int* h_exists)
+{
+    vpt_octnode* d_out = nullptr; int* d_ex = nullptr;
+    cudaError_t e = cudaMalloc(&d_out, sizeof(vpt_octnode) * kOctNodes);
+    if (e == cudaSuccess) e = cudaMemset(d_out, 0, sizeof(vpt_octnode) * kOctNodes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_ex, sizeof(int) * kOctNodes);
+    if (e == cudaSuccess) { k_octree_snapshot<<<(kOctNodes + 63) / 64, 64>>>(d_root, d_out, d_ex); e = cudaDeviceSynchronize(); }
+    if (e == cudaSuccess) e = cudaMemcpy(h_nodes, d_out, sizeof(vpt_octnode) * kOctNodes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_exists, d_ex, sizeof(int) * kOctNodes, cudaMemcpyDeviceToHost);
+    cudaFree(d_out); cudaFree(d_ex);
+    return e;
+}
+
 void instance_bounds_host(const vpt_gpu_vdb& g, float out6[6])
 {
     Box b = instance_bounds(g);

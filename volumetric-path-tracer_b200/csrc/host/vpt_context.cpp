@@ -26,6 +26,7 @@
 namespace vpt {
 cudaError_t octree_build_device(vpt_octnode* d_nodes, const vpt_gpu_vdb* d_vols, int n, cudaStream_t s);
 void instance_bounds_host(const vpt_gpu_vdb& g, float out6[6]);
+cudaError_t octree_snapshot(const vpt_octnode* d_root, vpt_octnode* h_nodes, int* h_exists);
 }
 
 static thread_local std::string g_last_error;
@@ -54,6 +55,11 @@ struct vpt_context {
     unsigned* d_counters = nullptr;   // [0] queue_count, [1] queue_head
     // stats
     unsigned long long launches = 0;
+    int count_stats = 0;              // option "count_stats": accumulate trace counters
+    unsigned long long* d_stats = nullptr;   // 8 counters
+    int profile = 0;                  // option "profile": CUDA-event timing of every kernel (debug / bench breakdown)
+    struct Ev { int kind; cudaEvent_t a, b; };
+    std::vector<Ev> events;
 };
 
 static int fail(vpt_context* ctx, int code, const std::string& msg) {
@@ -113,6 +119,8 @@ int vpt_create(vpt_context** out) {
     VPT_CUDA(c, cudaMalloc(&c->d_leaf_indices, sizeof(int) * vpt::kOctLeaves * VPT_OCT_MAX_VOLUMES));
     VPT_CUDA(c, cudaMalloc(&c->d_vrec, sizeof(vpt::VolumeRec) * VPT_OCT_MAX_VOLUMES));
     VPT_CUDA(c, cudaMalloc(&c->d_counters, sizeof(unsigned) * 4));
+    VPT_CUDA(c, cudaMalloc(&c->d_stats, sizeof(unsigned long long) * 8));
+    VPT_CUDA(c, cudaMemset(c->d_stats, 0, sizeof(unsigned long long) * 8));
     *out = c;
     return VPT_OK;
 }
@@ -120,6 +128,8 @@ int vpt_create(vpt_context** out) {
 void vpt_destroy(vpt_context* c) {
     if (!c) return;
     cudaFree(c->d_scene); cudaFree(c->d_internal); cudaFree(c->d_leaf_list); cudaFree(c->d_leaf_indices); cudaFree(c->d_vrec);
+    cudaFree(c->d_stats);
+    for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaFree(c->d_counters); cudaFree(c->d_queue); cudaFree(c->d_planeA); cudaFree(c->d_planeB); cudaFree(c->d_planeC); cudaFree(c->d_planeD);
     delete c;
 }
@@ -130,6 +140,8 @@ int vpt_set_option(vpt_context* c, const char* key, int value) {
     if (k == "passes_per_chunk") { if (value < 1 || value > 64) return fail(c, VPT_ERR_INVALID, "passes_per_chunk must be 1..64"); c->passes_per_chunk = value; }
     else if (k == "service_threshold") { if (value != 8 && value != 16 && value != 20 && value != 24 && value != 32) return fail(c, VPT_ERR_INVALID, "service_threshold must be one of 8,16,20,24,32"); c->service_threshold = value; }
     else if (k == "ctas_per_sm") { if (value < 0 || value > 8) return fail(c, VPT_ERR_INVALID, "ctas_per_sm must be 0..8"); c->ctas_per_sm = value; }
+    else if (k == "count_stats") { c->count_stats = value ? 1 : 0; }
+    else if (k == "profile") { c->profile = value ? 1 : 0; }
     else return fail(c, VPT_ERR_INVALID, "unknown option " + k);
     return VPT_OK;
 }
@@ -240,17 +252,28 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int trace_ctas = c->num_sms * ctas_per_sm;
 
+    fa.counters = c->count_stats ? c->d_stats : nullptr;
+    auto timed = [&](int kind, auto&& fn) -> cudaError_t {
+        if (!c->profile) return fn();
+        vpt_context::Ev ev; ev.kind = kind;
+        cudaEventCreate(&ev.a); cudaEventCreate(&ev.b);
+        cudaEventRecord(ev.a, stream);
+        cudaError_t e = fn();
+        cudaEventRecord(ev.b, stream);
+        c->events.push_back(ev);
+        return e;
+    };
     const uint32_t it0 = kp.iteration;
     unsigned done = 0;
     while (done < n_sampled) {
         const unsigned np = (n_sampled - done) < (unsigned)chunk ? (n_sampled - done) : (unsigned)chunk;
         fa.kp.iteration = it0 + done;
         VPT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned) * 2, stream));
-        VPT_CUDA(c, vpt::launch_generate(fa, (int)np, stream));          // reads the blue-noise state of pass `done`
-        VPT_CUDA(c, vpt::launch_trace(fa, trace_ctas, c->service_threshold, stream));
+        VPT_CUDA(c, timed(0, [&] { return vpt::launch_generate(fa, (int)np, stream); }));   // reads the blue-noise state of pass `done`
+        VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, trace_ctas, c->service_threshold, stream); }));
         const bool last = (done + np == n_passes);
-        VPT_CUDA(c, vpt::launch_resolve(fa, (int)np, 1, last ? 1 : 0, stream));
-        VPT_CUDA(c, vpt::launch_bn_advance((void*)kp.blue_noise_buffer, (int)np, stream));
+        VPT_CUDA(c, timed(2, [&] { return vpt::launch_resolve(fa, (int)np, 1, last ? 1 : 0, stream); }));
+        VPT_CUDA(c, timed(3, [&] { return vpt::launch_bn_advance((void*)kp.blue_noise_buffer, (int)np, stream); }));
         c->launches += 4;
         done += np;
     }
@@ -261,6 +284,31 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         VPT_CUDA(c, vpt::launch_bn_advance((void*)kp.blue_noise_buffer, (int)(n_passes - n_sampled), stream));
         c->launches += 2;
     }
+    return VPT_OK;
+}
+
+// Statistics accumulated since the last call (needs option "count_stats"): out[0..4] = volume lookups, lane-steps,
+// warp step iterations, lane transitions, warp transition rounds.  Synchronises the device.
+int vpt_get_counters(vpt_context* c, unsigned long long out[8], int reset) {
+    if (!c || !out) return VPT_ERR_INVALID;
+    VPT_CUDA(c, cudaDeviceSynchronize());
+    VPT_CUDA(c, cudaMemcpy(out, c->d_stats, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));
+    if (reset) VPT_CUDA(c, cudaMemset(c->d_stats, 0, sizeof(unsigned long long) * 8));
+    return VPT_OK;
+}
+
+// Per-kernel device time accumulated since the last call (needs option "profile"):
+// ms[0..3] = generate, trace, resolve, bn_advance; n[0..3] = launches of each.  Synchronises the device.
+int vpt_get_kernel_times(vpt_context* c, float ms[4], int n[4]) {
+    if (!c || !ms || !n) return VPT_ERR_INVALID;
+    VPT_CUDA(c, cudaDeviceSynchronize());
+    for (int i = 0; i < 4; ++i) { ms[i] = 0.f; n[i] = 0; }
+    for (auto& e : c->events) {
+        float t = 0.f; cudaEventElapsedTime(&t, e.a, e.b);
+        if (e.kind >= 0 && e.kind < 4) { ms[e.kind] += t; n[e.kind]++; }
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    c->events.clear();
     return VPT_OK;
 }
 
@@ -420,6 +468,13 @@ int vpt_octree_build(const vpt_gpu_vdb* h_volumes, int n, vpt_devptr_t* d_root_o
     cudaFree(d_vols);
     if (e != cudaSuccess) { cudaFree(d_nodes); return fail(nullptr, VPT_ERR_CUDA, std::string("vpt_octree_build: ") + cudaGetErrorString(e)); }
     *d_root_out = (vpt_devptr_t)(uintptr_t)d_nodes;
+    return VPT_OK;
+}
+
+int vpt_octree_read(vpt_devptr_t d_root, vpt_octnode* h_nodes585, int* h_exists585) {
+    if (!d_root || !h_nodes585 || !h_exists585) return fail(nullptr, VPT_ERR_INVALID, "vpt_octree_read: null argument");
+    cudaError_t e = vpt::octree_snapshot(reinterpret_cast<const vpt_octnode*>((uintptr_t)d_root), h_nodes585, h_exists585);
+    if (e != cudaSuccess) return fail(nullptr, VPT_ERR_CUDA, std::string("vpt_octree_read: ") + cudaGetErrorString(e));
     return VPT_OK;
 }
 

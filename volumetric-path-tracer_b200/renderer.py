@@ -98,6 +98,21 @@ class Renderer:
         check(lib.vpt_get_stats(self.ctx, C.byref(n), C.byref(q) if with_queue else None), self.ctx, "vpt_get_stats")
         return int(n.value), int(q.value)
 
+    def set_option(self, key, value):
+        check(lib.vpt_set_option(self.ctx, key.encode(), int(value)), self.ctx, f"vpt_set_option({key})")
+
+    def counters(self, reset=True):
+        out = (C.c_ulonglong * 8)()
+        check(lib.vpt_get_counters(self.ctx, out, 1 if reset else 0), self.ctx, "vpt_get_counters")
+        v = list(out)
+        return dict(lookups=v[0], lane_steps=v[1], warp_step_iters=v[2], lane_transitions=v[3], warp_transition_rounds=v[4])
+
+    def kernel_times(self):
+        ms = (C.c_float * 4)(); n = (C.c_int * 4)()
+        check(lib.vpt_get_kernel_times(self.ctx, ms, n), self.ctx, "vpt_get_kernel_times")
+        names = ("generate", "trace", "resolve", "bn_advance")
+        return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}
+
     def accum_image(self):
         """(H, W, 3) float32 linear radiance (single rank only)."""
         assert self.n_ranks == 1
