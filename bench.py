@@ -127,7 +127,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=0, help="passes fused per kernel round (0 = library default)")
-    ap.add_argument("--threshold", type=int, default=0, help="trace service threshold (0 = library default)")
+    ap.add_argument("--sched-min-lanes", type=int, default=0, help="trace scheduler threshold (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -185,7 +185,7 @@ def main():
     # ------------------------------------------------------------------------------------------ ours
     opts = {}
     if args.chunk: opts["passes_per_chunk"] = args.chunk
-    if args.threshold: opts["service_threshold"] = args.threshold
+    if args.sched_min_lanes: opts["sched_min_lanes"] = args.sched_min_lanes
     stream = torch.cuda.current_stream().cuda_stream
     if world > 1:
         dr = V.DistributedRenderer(scene, WIDTH, HEIGHT, kp=kp, stripe_rows=8, options=opts)
@@ -250,7 +250,7 @@ def main():
         roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": peak_src, "bytes_per_sample": bytes_per_sample,
                     "density_lookups_per_sample": lookups_per_sample, "samples_per_launch": samples_per_launch,
-                    "avg_launch_ms": t_trace, "step_loop_simt_efficiency": simt,
+                    "avg_launch_ms": t_trace, "step_loop_simt_efficiency": simt, "trace_counters": cnt,
                     "kernel_ms_per_step": {k: v["ms"] / 2 for k, v in kt.items()},
                     "note": "dragon.vdb is 425 KB: L2/TEX resident, so the HBM fraction is small by construction (SURVEY 8(d)); "
                             "the path is latency/ALU bound, see profiles/"}

@@ -102,6 +102,10 @@ int vptref_bn_advance(const void* kernel_params, int sync) {
 int vptref_build_octree(const void* h_volumes, int n, void** d_root_out) {
     const GPU_VDB* vdbs = reinterpret_cast<const GPU_VDB*>(h_volumes);
     if (n < 1 || n > 600) { fprintf(stderr, "[vptref] octree: n=%d outside the reference's 1..600 range\n", n); return -3; }
+    // every reference octree takes 585 x 2520 B from the device heap and is never freed by the reference;
+    // the default 8 MB heap is exhausted after five builds (then `new` returns NULL and the build kernel faults)
+    static bool heap_set = false;
+    if (!heap_set) { cudaDeviceSetLimit(cudaLimitMallocHeapSize, (size_t)512 << 20); cudaGetLastError(); heap_set = true; }
     GPU_VDB* d_vols = nullptr;
     CKR(cudaMalloc(&d_vols, n * sizeof(GPU_VDB)));
     CKR(cudaMemcpy(d_vols, vdbs, n * sizeof(GPU_VDB), cudaMemcpyHostToDevice));

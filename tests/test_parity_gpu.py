@@ -185,7 +185,7 @@ def test_partition_invariance_and_determinism(dragon):
     parts = []
     for rank in range(4):
         r = V.Renderer(scene, W, H, kp=make_kp(ray_depth=2), cam=one.cam, rank=rank, n_ranks=4, stripe_rows=8,
-                       options=dict(service_threshold=(8, 16, 24, 32)[rank], passes_per_chunk=rank + 1))
+                       options=dict(sched_min_lanes=(1, 8, 16, 32)[rank], passes_per_chunk=rank + 1))
         scene.reset_blue_noise(); r.render(3); parts.append(r)
     torch.cuda.synchronize()
     gathered = torch.cat([p.buffers.accum for p in parts], dim=0)

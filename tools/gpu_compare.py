@@ -28,7 +28,7 @@ def main():
         kp = V.default_kernel_params(); kp.environment_type = 1; kp.ray_depth = int(kv.get("ray_depth", 1)); kp.volume_depth = int(kv.get("volume_depth", 1))
         kp.max_interactions = 1000; kp.phase_g1 = float(kv.get("g", 0.0)); kp.density_mult = float(kv.get("density_mult", 1.0)); kp.tr_depth = float(kv.get("tr_depth", 1.0))
         return kp
-    opts = {k: int(v) for k, v in kv.items() if k in ("passes_per_chunk", "service_threshold", "ctas_per_sm")}
+    opts = {k: int(v) for k, v in kv.items() if k in ("passes_per_chunk", "sched_min_lanes", "ctas_per_sm", "debug_flags")}
     mine = V.Renderer(scene, W, H, kp=mk(), options=opts)
     ref = V.Renderer(scene, W, H, kp=mk(), cam=mine.cam)
     orc = RefOracle()

@@ -1,0 +1,23 @@
+#!/usr/bin/env python3
+"""Summarise an ncu report per CUDA source line: instructions, avg active threads, stall samples.
+usage: tools/ncu_lines.py report.ncu-rep [kernel-regex] [top N]"""
+import csv, subprocess, sys, io, collections
+rep = sys.argv[1]; top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+cur_file = None; hdr = None; agg = collections.OrderedDict(); tot_i = tot_t = tot_s = 0
+for r in rows:
+    if len(r) >= 2 and r[0] == "File Path": cur_file = r[1].split("/")[-1]; continue
+    if len(r) >= 2 and r[0] == "Function Name": continue
+    if r and r[0] == "Line No": hdr = {h: i for i, h in enumerate(r)}; idx_src2 = [i for i, h in enumerate(r) if h == "Source"]; continue
+    if hdr is None or not r or r[0] in ("", "0") or len(r) < len(hdr): continue
+    try:
+        ln = int(r[0]); inst = float(r[hdr["Instructions Executed"]]); thr = float(r[hdr["Thread Instructions Executed"]]); smp = float(r[hdr["# Samples"]])
+    except ValueError:
+        continue
+    key = (cur_file, ln, r[1].strip()[:90])
+    a = agg.setdefault(key, [0, 0, 0]); a[0] += inst; a[1] += thr; a[2] += smp
+    tot_i += inst; tot_t += thr; tot_s += smp
+print(f"total warp-inst {tot_i:.3g}  thread-inst {tot_t:.3g}  avg active {tot_t/max(tot_i,1):.1f}  samples {tot_s:.0f}")
+for (f, ln, src), (i, t, s) in sorted(agg.items(), key=lambda kv: -kv[1][2])[:top]:
+    print(f"{100*s/max(tot_s,1):5.1f}% smp {100*i/max(tot_i,1):5.1f}% inst  act {t/max(i,1):5.1f}  {f}:{ln:<4d} {src}")

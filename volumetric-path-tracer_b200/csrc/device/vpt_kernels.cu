@@ -19,6 +19,8 @@
 
 namespace vpt {
 
+constexpr int kRefillLanes = 8;      // idle lanes that justify the queue atomic
+
 // =====================================================================================================
 // k_prepare_scene
 // =====================================================================================================
@@ -131,6 +133,7 @@ __global__ void k_prepare_scene(const vpt_gpu_vdb* __restrict__ vols, const vpt_
 struct FrameShared {
     SceneTables sc;
     OctShared   oct;
+    VolumeRec   vol0;      // volume 0 staged for single-volume scenes (the headline case)
 };
 
 VPT_DEV void load_frame_shared(FrameShared& fs, const SceneTables* sc_dev) {
@@ -141,6 +144,11 @@ VPT_DEV void load_frame_shared(FrameShared& fs, const SceneTables* sc_dev) {
     const uint4* src = reinterpret_cast<const uint4*>(fs.sc.internal);
     uint4* d = reinterpret_cast<uint4*>(fs.oct.node);
     for (int i = t; i < kOctInternalNodes * 3; i += nt) d[i] = __ldg(src + i);
+    {   // 96-byte record of volume 0
+        const uint4* vs = reinterpret_cast<const uint4*>(fs.sc.volumes);
+        uint4* vd = reinterpret_cast<uint4*>(&fs.vol0);
+        for (int i = t; i < (int)(sizeof(VolumeRec) / 16); i += nt) vd[i] = __ldg(vs + i);
+    }
     __syncthreads();
 }
 
@@ -166,7 +174,7 @@ VPT_DEV float van_der_corput(Rng& rng) {
     float rand_int = 0, denom = 1, invBase = 1.f / BASE;
     while (n) {
         denom *= BASE;
-        rand_int += (n % BASE) / denom;
+        rand_int = padd(rand_int, __fdividef((float)(n % BASE), denom));
         n *= invBase;
     }
     return rand_int;
@@ -193,6 +201,7 @@ k_generate(const FrameArgs fa)
     bool hit = false;
     float3 org = f3(0.f), dir = f3(0.f, 0.f, 1.f);
     uint32_t kdraws = 0;
+    int obj = 0; float t_min = 0.f;
     const uint32_t lp = (uint32_t)lr * (uint32_t)g.width + (uint32_t)x;
 
     if (valid) {
@@ -201,35 +210,32 @@ k_generate(const FrameArgs fa)
         const uint32_t idx = (uint32_t)y * (uint32_t)g.width + (uint32_t)x;
         Rng rng; rng.init(idx, kp.iteration + (uint32_t)pass, 0u);
 
-        // blue-noise jitter; the buffer holds the state at the first pass of the chunk
+        // blue-noise jitter of this pass, from the per-chunk table written by k_bn_prepare
         const int bn_index = (y % 256) * 256 + (x % 256);
-        const float3* bnbuf = reinterpret_cast<const float3*>(kp.blue_noise_buffer);
-        float bnx = bnbuf[bn_index].x, bny = bnbuf[bn_index].y;
-        for (int i = 0; i < pass; ++i) {
-            bnx += (1.0f + sqrtf(5.0f)) / 2.0f; bnx = fmodf(bnx, 1.0f);
-            bny += (1.0f + sqrtf(5.0f)) / 2.0f; bny = fmodf(bny, 1.0f);
-        }
-        const float u = float(x + bnx) / float(kp.resolution.x);
-        const float v = float(y + bny) / float(kp.resolution.y);
+        const float2 bnv = __ldg(fa.bn_table + (size_t)pass * 65536 + bn_index);
+        const float bnx = bnv.x, bny = bnv.y;
+        const float u = __fdividef(padd((float)x, bnx), (float)kp.resolution.x);
+        const float v = __fdividef(padd((float)y, bny), (float)kp.resolution.y);
 
         // thin-lens ray (reference camera::get_ray, camera.h:131-136)
         float3 p;
         do {
             const float a = van_der_corput<2>(rng);
             const float b = van_der_corput<3>(rng);
-            p = 2.0f * f3(a, b, 0) - f3(1.0f, 1.0f, 0.0f);
-        } while (dot(p, p) >= 1.0);
-        const float3 rd = cam.lens_radius * p;
-        const float3 offset = ld3(cam.u) * rd.x + ld3(cam.v) * rd.y;
+            p = f3(pfma(a, 2.0f, -1.0f), pfma(b, 2.0f, -1.0f), 0.0f);
+        } while (pfma(p.x, p.x, pmul(p.y, p.y)) >= 1.0f);
+        const float3 rd = f3(pmul(cam.lens_radius, p.x), pmul(cam.lens_radius, p.y), 0.0f);
+        const float3 offset = f3(pfma(cam.u.x, rd.x, pmul(cam.v.x, rd.y)), pfma(cam.u.y, rd.x, pmul(cam.v.y, rd.y)), pfma(cam.u.z, rd.x, pmul(cam.v.z, rd.y)));
         (void)rng.next();                                        // shutter time draw (value unused by the path)
-        org = ld3(cam.origin) + offset;
-        const float3 b = ld3(cam.lower_left_corner) + u * ld3(cam.horizontal) + v * ld3(cam.vertical) - ld3(cam.origin) - offset;
+        org = f3(padd(cam.origin.x, offset.x), padd(cam.origin.y, offset.y), padd(cam.origin.z, offset.z));
+        const float3 b = f3(psub(psub(pfma(cam.vertical.x, v, pfma(cam.horizontal.x, u, cam.lower_left_corner.x)), cam.origin.x), offset.x),
+                            psub(psub(pfma(cam.vertical.y, v, pfma(cam.horizontal.y, u, cam.lower_left_corner.y)), cam.origin.y), offset.y),
+                            psub(psub(pfma(cam.vertical.z, v, pfma(cam.horizontal.z, u, cam.lower_left_corner.z)), cam.origin.z), offset.z));
         dir = normalize(b);
         kdraws = rng.k;
 
         const SphereRec sph = load_sphere(fa.sphere);
-        float t_min;
-        const int obj = closest_object(sc, sph, org, dir, t_min);
+        obj = closest_object(sc, sph, org, dir, t_min);
         hit = (obj != 0);
 
         if (!hit) {
@@ -248,385 +254,16 @@ k_generate(const FrameArgs fa)
         if (lane == __ffs(m) - 1) base = atomicAdd(fa.queue_count, __popc(m));
         base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
         if (hit) {
+            // 24-byte record (+16 B origin when the lens is not a pinhole): direction + entry distance, ids + RNG position
             const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
-            float4* q = fa.queue + 2 * (size_t)slot;
-            q[0] = make_float4(org.x, org.y, org.z, dir.x);
-            q[1] = make_float4(dir.y, dir.z, __uint_as_float(lp), __uint_as_float((uint32_t)pass | (kdraws << 8)));
+            fa.queue_dir[slot] = make_float4(dir.x, dir.y, dir.z, t_min);
+            fa.queue_id[slot] = make_uint2(lp, (uint32_t)pass | (kdraws << 6) | ((uint32_t)obj << 16));
+            if (fa.queue_org) fa.queue_org[slot] = make_float4(org.x, org.y, org.z, 0.f);
         }
     }
 }
 
-// =====================================================================================================
-// k_trace -- persistent wavefront over the hit queue
-// =====================================================================================================
-enum WalkMode : int { W_NONE = 0, W_DELTA = 1, W_RATIO = 2, W_EMIT = 3 };
-enum Phase : int {
-    PH_IDLE = 0,          // lane has no ray
-    PH_BOUNCE,            // top of a ray_depth iteration
-    PH_VOL_ITER,          // start a delta-tracking walk
-    PH_AFTER_DELTA,       // delta walk ended
-    PH_VOL_DONE,          // volume_depth loop finished
-    PH_AFTER_SUN,         // ratio walk toward the sun ended
-    PH_POINT_NEXT,        // next point-light iteration
-    PH_AFTER_POINT,       // ratio walk toward a point light ended
-    PH_EMISSION,          // maybe start the emission walk
-    PH_AFTER_EMIT,
-    PH_AFTER_VOLUME,      // second closest-object test of the bounce
-    PH_AFTER_SPHERE_TR,   // ratio walk from the sphere toward the sun ended
-    PH_FINISH
-};
-enum ExitReason : int { EX_NONE = 0, EX_OUTSIDE, EX_DISTANCE, EX_SCATTER, EX_TR_DONE };
-
-struct PathState {
-    // ray
-    float3 pos, dir;
-    float3 org;           // camera-ray origin (depth reference + default env_pos)
-    float3 env_pos;
-    float3 beta, L;
-    float  alpha;         // the reference's `tr` out-parameter (accumulated density, capped at 1)
-    float  depth;
-    // walk
-    float3 wpos, wdir;    // position / direction of the running walk (Tr and emission walk on copies)
-    float  t, distance;
-    float  trv;           // running residual-ratio transmittance (all three channels equal)
-    float  T_c;
-    float3 emis;          // emission walk accumulator
-    float3 thr;           // throughput returned by the last delta walk
-    int    mode, phase, exit_reason;
-    // loop counters
-    int    rd, vd, light_budget, light_index;
-    float3 Ld;            // point-light accumulator
-    float3 sph_normal;
-    bool   mi, first_walk, geo;
-    int    obj;
-    uint32_t lp, pass;
-    uint32_t nlook;       // density / emission lookups issued by this lane (statistics)
-    Rng    rng;
-};
-
-struct TraceConsts {
-    float inv_max, inv_mult, sigma_c, sigma_r_inv;
-    float3 sun_dir;
-};
-
-// One unified tracking step.  Returns with st.mode == W_NONE when the walk has ended (st.exit_reason set).
-VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph)
-{
-    const SceneTables& sc = fs.sc;
-    const vpt_kernel_params& kp = fa.kp;
-    const int leaf = oct_locate_or_skip(fs.oct, sc, st.wpos, st.wdir);
-    if (leaf == -2) return;                                   // skipped an empty node, no draw consumed
-    if (leaf == -1) { st.mode = W_NONE; st.exit_reason = EX_OUTSIDE; return; }
-
-    if (st.mode == W_DELTA) {
-        // distance to the box exit (or to the sphere) from the CURRENT position, every step (:1647-1651)
-        float t_min, t_max, geo_dist = .0f;
-        aabb_intersect(sc.root_pmin, sc.root_pmax, st.wpos, st.wdir, t_min, st.distance);
-        if (sphere_intersect(sph, st.wpos, st.wdir, geo_dist, t_max)) { st.distance = geo_dist; st.geo = true; }
-        st.t -= logf(1 - st.rng.next()) * tc.inv_max * tc.inv_mult;
-        if (st.t >= st.distance) { st.mode = W_NONE; st.exit_reason = EX_DISTANCE; return; }
-    } else if (st.mode == W_RATIO) {
-        st.t -= logf(1 - st.rng.next()) * tc.sigma_r_inv * kp.tr_depth;
-        if (st.t >= st.distance) { st.mode = W_NONE; st.exit_reason = EX_DISTANCE; return; }
-    } else {
-        float inv_max_density = 1 / sc.max_extinction;
-        st.t -= logf(1 - st.rng.next()) * inv_max_density * kp.tr_depth / kp.extinction.x;
-    }
-
-    st.wpos += st.wdir * st.t;                                // cumulative t, never reset (quirk Q2)
-    if (!aabb_contains(sc.root_pmin, sc.root_pmax, st.wpos)) { st.mode = W_NONE; st.exit_reason = EX_OUTSIDE; return; }
-
-    st.nlook++;
-    if (st.mode == W_EMIT) {
-        st.emis += leaf_emission(sc, leaf, st.wpos, reinterpret_cast<const float3*>(kp.emission_texture), kp.emission_pivot, kp.emission_scale);
-        return;
-    }
-
-    const float density = leaf_density(sc, leaf, st.wpos);
-    if (st.mode == W_DELTA) {
-        const float3 Cd = leaf_color(sc, leaf, st.wpos);
-        const int index = int(floorf(fminf(fmaxf((density * tc.inv_max * 255.0f / kp.emission_pivot), 0.0f), 255.0f)));
-        const float3 density_color = reinterpret_cast<const float3*>(kp.density_color_texture)[index];
-        if (st.alpha < 1.0f) st.alpha += density;
-        if (density * tc.inv_max > st.rng.next()) {
-            st.thr = (ld3(kp.albedo) * Cd * density_color / ld3(kp.extinction)) * float(kp.energy_inject);
-            st.mode = W_NONE; st.exit_reason = EX_SCATTER;
-        }
-    } else {
-        st.trv *= 1 - ((density - tc.sigma_c) * tc.sigma_r_inv);
-        if (length(f3(st.trv)) < VPT_EPS) { st.mode = W_NONE; st.exit_reason = EX_TR_DONE; }
-    }
-}
-
-// Set up a residual-ratio walk from (p, d) (reference Tr prologue, :1150-1167).
-// Returns false when the transmittance is already known (then `result` holds it).
-VPT_DEV bool begin_ratio_walk(PathState& st, const FrameShared& fs, const TraceConsts& tc, const SphereRec& sph,
-                              float3 p, float3 d, float& result)
-{
-    const SceneTables& sc = fs.sc;
-    float t_min, t_max, geo_dist = .0f, distance = .0f;
-    if (!aabb_contains(sc.root_pmin, sc.root_pmax, p)) {
-        if (aabb_intersect(sc.root_pmin, sc.root_pmax, p, d, t_min, t_max)) p += d * (t_min + VPT_EPS);
-        else { result = 1.0f; return false; }
-    }
-    aabb_intersect(sc.root_pmin, sc.root_pmax, p, d, t_min, distance);
-    if (sphere_intersect(sph, p, d, geo_dist, t_max)) { result = 0.0f; return false; }
-    st.T_c = expf(-tc.sigma_c * distance);
-    st.wpos = p; st.wdir = d; st.t = 0.0f; st.distance = distance; st.trv = 1.0f;
-    st.mode = W_RATIO;
-    return true;
-}
-
-VPT_DEV float finish_ratio_walk(const PathState& st) { return clampf(st.trv * st.T_c, .0f, 1.0f); }
-
-// Estimator transitions.  Runs until the lane either starts a walk (st.mode != W_NONE) or retires.
-VPT_DEV void transition(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph)
-{
-    const SceneTables& sc = fs.sc;
-    const vpt_kernel_params& kp = fa.kp;
-    const FrameGeom& g = fa.geom;
-
-    for (;;) {
-        switch (st.phase) {
-        case PH_BOUNCE: {
-            if (st.rd > kp.ray_depth) { st.phase = PH_FINISH; break; }
-            float t_min;
-            st.obj = closest_object(sc, sph, st.pos, st.dir, t_min);
-            if (st.first_walk && st.obj != 1) {                    // depth pass without a volume walk (:1883-1888)
-                if (st.obj == 2) st.depth = length(st.org - (st.pos + st.dir * t_min));
-                st.first_walk = false;
-            }
-            if (st.obj == 0) { st.phase = PH_FINISH; break; }      // nothing ahead: every later bounce is a no-op
-            if (st.obj == 1) {
-                st.pos += st.dir * (t_min + VPT_EPS);
-                st.vd = 1;
-                st.phase = PH_VOL_ITER;
-            } else st.phase = PH_AFTER_VOLUME;
-            break;
-        }
-        case PH_VOL_ITER: {
-            if (st.vd > kp.volume_depth) { st.phase = PH_VOL_DONE; break; }
-            st.mi = false;
-            st.wpos = st.pos; st.wdir = st.dir; st.t = 0.0f; st.distance = .0f; st.geo = false;
-            st.mode = W_DELTA; st.phase = PH_AFTER_DELTA;
-            return;
-        }
-        case PH_AFTER_DELTA: {
-            st.pos = st.wpos;                                      // `sample` advances the caller's ray_pos
-            if (st.exit_reason == EX_SCATTER) { st.beta *= st.thr; st.mi = true; }
-            else st.beta *= f3(1.0f);
-            if (st.exit_reason == EX_DISTANCE) st.obj = 2;          // compiled reference sets obj = 2 on every distance exit (Q4)
-            if (st.first_walk) {
-                st.depth = st.mi ? length(st.org - st.pos) : .0f;
-                // the reference runs this identical walk twice (depth pass + integrator) and accumulates
-                // `tr` in both; the second replay adds the same densities again while tr < 1
-                if (st.alpha < 1.0f) st.alpha += st.alpha;
-                st.first_walk = false;
-            }
-            if (is_black(st.beta) || st.obj == 2) { st.phase = PH_VOL_DONE; break; }
-            if (st.mi) hg_sample(st.dir, st.rng, kp.phase_g1);
-            st.vd++;
-            st.phase = PH_VOL_ITER;
-            break;
-        }
-        case PH_VOL_DONE: {
-            if (st.mi) {
-                float res;
-                if (begin_ratio_walk(st, fs, tc, sph, st.pos, tc.sun_dir, res)) { st.phase = PH_AFTER_SUN; return; }
-                st.trv = res; st.T_c = 1.0f; st.exit_reason = EX_NONE;
-                st.phase = PH_AFTER_SUN;
-                // fall through with a "finished" walk whose result is res
-                st.mode = W_NONE;
-                // encode the known result so that finish_ratio_walk returns it unchanged
-                // (res is 0 or 1, clamp(res * 1) == res)
-                break;
-            }
-            st.phase = PH_EMISSION;
-            break;
-        }
-        case PH_AFTER_SUN: {
-            const float tr = finish_ratio_walk(st);
-            const float cos_theta = dot(st.dir, tc.sun_dir);
-            const float phase_pdf = hg_phase(cos_theta, kp.phase_g1);
-            const float3 Ld = f3(tr) * phase_pdf;
-            st.L += Ld * ld3(kp.sun_color) * kp.sun_mult * st.beta;
-            if (fa.lights.num_lights > 0) { st.Ld = f3(.0f); st.light_budget = 10; st.phase = PH_POINT_NEXT; }
-            else st.phase = PH_EMISSION;
-            break;
-        }
-        case PH_POINT_NEXT: {
-            if (st.light_budget < 0) { st.L += st.Ld * st.beta; st.phase = PH_EMISSION; break; }
-            const vpt_point_light* lp = reinterpret_cast<const vpt_point_light*>(fa.lights.light_ptr);
-            st.light_index = int(floorf(st.rng.next() * fa.lights.num_lights));
-            const float3 d = normalize(ld3(lp[st.light_index].pos) - st.pos);
-            float res;
-            if (begin_ratio_walk(st, fs, tc, sph, st.pos, d, res)) { st.phase = PH_AFTER_POINT; return; }
-            st.trv = res; st.T_c = 1.0f; st.mode = W_NONE;
-            st.phase = PH_AFTER_POINT;
-            break;
-        }
-        case PH_AFTER_POINT: {
-            const float tr = finish_ratio_walk(st);
-            if (st.light_budget < (int)fa.lights.num_lights) {       // reference point_light::Le, light.h:104-121
-                const vpt_point_light& pl = reinterpret_cast<const vpt_point_light*>(fa.lights.light_ptr)[st.light_index];
-                const float3 lpos = ld3(pl.pos);
-                const float3 wi = normalize(lpos - st.pos);
-                const float cos_theta = dot(st.dir, wi);
-                const float phase_pdf = hg_phase(cos_theta, kp.phase_g1);
-                const float sqr_dist = length(lpos * lpos - st.pos * st.pos);
-                const float falloff = 1 / sqr_dist;
-                st.Ld += ld3(pl.color) * pl.power * f3(tr) * phase_pdf * falloff;
-            }
-            st.light_budget--;
-            st.phase = PH_POINT_NEXT;
-            break;
-        }
-        case PH_EMISSION: {
-            if (kp.emission_scale > 0 && st.mi) {
-                st.wpos = st.pos; st.wdir = st.dir; st.t = 0.0f; st.emis = f3(.0f);
-                st.mode = W_EMIT; st.phase = PH_AFTER_EMIT;
-                return;
-            }
-            st.phase = PH_AFTER_VOLUME;
-            break;
-        }
-        case PH_AFTER_EMIT: {
-            st.L += st.emis;
-            st.phase = PH_AFTER_VOLUME;
-            break;
-        }
-        case PH_AFTER_VOLUME: {
-            float t_min;
-            st.obj = closest_object(sc, sph, st.pos, st.dir, t_min);
-            if (st.obj == 2) {                                     // diffuse/mirror bounce off the reference sphere (:1807-1834)
-                st.pos += st.dir * t_min;
-                const float3 normal = normalize((st.pos - sph.center) / sph.radius);
-                const float3 nl = dot(normal, st.dir) < 0 ? normal : normal * -1;
-                const float phi = 2 * VPT_PI_F * st.rng.next();
-                const float r2 = st.rng.next();
-                const float r2s = sqrtf(r2);
-                const float3 w = normalize(nl);
-                const float3 u = normalize(cross((fabs(w.x) > .1 ? f3(0, 1, 0) : f3(1, 0, 0)), w));
-                const float3 v = cross(w, u);
-                const float3 hemisphere_dir = normalize(u * cosf(phi) * r2s + v * sinf(phi) * r2s + w * sqrtf(1 - r2));
-                const float3 ref = reflect3(st.dir, nl);
-                st.dir = lerp3(ref, hemisphere_dir, sph.roughness);
-                st.pos += normal * VPT_EPS;
-                st.beta *= sph.color;
-                st.sph_normal = normal;
-                float res;
-                if (begin_ratio_walk(st, fs, tc, sph, st.pos, tc.sun_dir, res)) { st.phase = PH_AFTER_SPHERE_TR; return; }
-                st.trv = res; st.T_c = 1.0f; st.mode = W_NONE;
-                st.phase = PH_AFTER_SPHERE_TR;
-                break;
-            }
-            st.rd++;
-            st.phase = PH_BOUNCE;
-            break;
-        }
-        case PH_AFTER_SPHERE_TR: {
-            const float v_tr = finish_ratio_walk(st);
-            st.L += ld3(kp.sun_color) * kp.sun_mult * f3(v_tr) * fmaxf(dot(tc.sun_dir, st.sph_normal), .0f) * st.beta;
-            st.env_pos = st.pos;
-            st.rd++;
-            st.phase = PH_BOUNCE;
-            break;
-        }
-        case PH_FINISH: {
-            const size_t s = (size_t)st.pass * g.n_local + st.lp;
-            fa.planeA[s] = make_float4(st.dir.x, st.dir.y, st.dir.z, st.alpha);
-            fa.planeB[s] = make_float4(st.L.x, st.L.y, st.L.z, st.depth);
-            fa.planeC[s] = make_float4(st.beta.x, st.beta.y, st.beta.z, 1.f);
-            if (fa.planeD) fa.planeD[s] = make_float4(st.env_pos.x, st.env_pos.y, st.env_pos.z, 0.f);
-            st.phase = PH_IDLE;
-            return;
-        }
-        default:
-            return;
-        }
-    }
-}
-
-template <int kServiceThreshold>
-__global__ void __launch_bounds__(kTraceThreads, 2)
-k_trace(const FrameArgs fa)
-{
-    __shared__ FrameShared fs;
-    load_frame_shared(fs, fa.scene);
-    const SceneTables& sc = fs.sc;
-    const vpt_kernel_params& kp = fa.kp;
-    const FrameGeom& g = fa.geom;
-    const int lane = threadIdx.x & 31;
-
-    TraceConsts tc;
-    tc.inv_max = 1.0f / sc.max_extinction;
-    tc.inv_mult = 1.0f / kp.density_mult;
-    tc.sigma_c = sc.min_extinction;
-    tc.sigma_r_inv = 1.0f / (sc.max_extinction - tc.sigma_c);
-    tc.sun_dir = sun_direction(kp.azimuth, kp.elevation);
-    const SphereRec sph = load_sphere(fa.sphere);
-
-    const unsigned q_count = *fa.queue_count;
-    PathState st;
-    st.phase = PH_IDLE; st.mode = W_NONE; st.nlook = 0;
-    bool queue_dry = false;
-    uint32_t lane_steps = 0, warp_iters = 0, lane_trans = 0, warp_trans = 0;
-
-    for (;;) {
-        // ---- refill idle lanes from the ray queue (one atomic per warp) ----
-        const unsigned idle = __ballot_sync(0xffffffffu, st.phase == PH_IDLE);
-        if (idle && !queue_dry) {
-            unsigned base = 0;
-            const int leader = __ffs(idle) - 1;
-            if (lane == leader) base = atomicAdd(fa.queue_head, __popc(idle));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (base + __popc(idle) >= q_count) queue_dry = true;
-            if (st.phase == PH_IDLE) {
-                const unsigned slot = base + __popc(idle & ((1u << lane) - 1u));
-                if (slot < q_count) {
-                    const float4 r0 = __ldg(fa.queue + 2 * (size_t)slot), r1 = __ldg(fa.queue + 2 * (size_t)slot + 1);
-                    st.org = f3(r0.x, r0.y, r0.z); st.dir = f3(r0.w, r1.x, r1.y);
-                    st.lp = __float_as_uint(r1.z);
-                    const uint32_t pk = __float_as_uint(r1.w);
-                    st.pass = pk & 0xffu;
-                    const uint32_t lr = st.lp / (uint32_t)g.width, x = st.lp - lr * (uint32_t)g.width;
-                    const uint32_t idx = (uint32_t)global_row(g, (int)lr) * (uint32_t)g.width + x;
-                    st.rng.init(idx, kp.iteration + st.pass, pk >> 8);
-                    st.pos = st.org; st.env_pos = st.org;
-                    st.beta = f3(1.0f); st.L = f3(.0f); st.alpha = .0f; st.depth = .0f;
-                    st.mi = false; st.first_walk = true; st.rd = 1; st.obj = 0;
-                    st.phase = PH_BOUNCE; st.mode = W_NONE;
-                }
-            }
-        }
-        if (__ballot_sync(0xffffffffu, st.phase != PH_IDLE) == 0u) break;
-
-        // ---- estimator transitions for every lane that is between walks ----
-        if (st.phase != PH_IDLE && st.mode == W_NONE) { transition(st, fs, fa, tc, sph); lane_trans++; }
-        warp_trans++;
-
-        // ---- converged step loop: keep stepping while enough lanes are inside a walk ----
-        for (;;) {
-            const unsigned walking = __ballot_sync(0xffffffffu, st.mode != W_NONE);
-            if (walking == 0u) break;
-            const unsigned waiting = __ballot_sync(0xffffffffu, st.mode == W_NONE && (st.phase != PH_IDLE || !queue_dry));
-            if (waiting != 0u && __popc(walking) < kServiceThreshold) break;
-            if (st.mode != W_NONE) { walk_step(st, fs, fa, tc, sph); lane_steps++; }
-            warp_iters++;
-        }
-    }
-
-    if (fa.counters) {                                        // optional statistics (one atomic set per warp)
-        unsigned long long a = st.nlook, b = lane_steps, c = lane_trans;
-        for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o);
-        }
-        if (lane == 0) {
-            atomicAdd(fa.counters + 0, a); atomicAdd(fa.counters + 1, b); atomicAdd(fa.counters + 2, (unsigned long long)warp_iters);
-            atomicAdd(fa.counters + 3, c); atomicAdd(fa.counters + 4, (unsigned long long)warp_trans);
-        }
-    }
-}
+#include "vpt_trace.cuh"
 
 // =====================================================================================================
 // k_resolve
@@ -724,6 +361,21 @@ k_resolve(const FrameArgs fa, const int n_passes, const int sampled, const int w
 // =====================================================================================================
 // k_bn_advance: blue-noise buffer += golden ratio (mod 1), `n` passes worth (:2319-2325)
 // =====================================================================================================
+// Per-chunk jitter table: table[p][i] = (x, y) of blue-noise entry i after p advances, p = 0..np-1; the buffer
+// itself is left advanced by `np` passes.  One launch replaces the per-thread replay in k_generate.
+__global__ void k_bn_prepare(float3* bn, float2* table, int np)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 256 * 256) return;
+    float3 val = bn[idx];
+    for (int i = 0; i < np; ++i) {
+        table[(size_t)i * 65536 + idx] = make_float2(val.x, val.y);
+        val.x += (1.0f + sqrtf(5.0f)) / 2.0f; val.y += (1.0f + sqrtf(5.0f)) / 2.0f; val.z += (1.0f + sqrtf(5.0f)) / 2.0f;
+        val.x = fmodf(val.x, 1.0f); val.y = fmodf(val.y, 1.0f); val.z = fmodf(val.z, 1.0f);
+    }
+    bn[idx] = val;
+}
+
 __global__ void k_bn_advance(float3* bn, int n)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -771,28 +423,16 @@ cudaError_t launch_generate(const FrameArgs& fa, int n_passes, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_trace(const FrameArgs& fa, int n_ctas, int service_threshold, cudaStream_t s)
+cudaError_t launch_trace(const FrameArgs& fa, int n_ctas, cudaStream_t s)
 {
-    switch (service_threshold) {
-    case 8:  k_trace<8><<<n_ctas, kTraceThreads, 0, s>>>(fa); break;
-    case 16: k_trace<16><<<n_ctas, kTraceThreads, 0, s>>>(fa); break;
-    case 24: k_trace<24><<<n_ctas, kTraceThreads, 0, s>>>(fa); break;
-    case 32: k_trace<32><<<n_ctas, kTraceThreads, 0, s>>>(fa); break;
-    default: k_trace<20><<<n_ctas, kTraceThreads, 0, s>>>(fa); break;
-    }
+    k_trace<<<n_ctas, kTraceThreads, 0, s>>>(fa);
     return cudaGetLastError();
 }
 
-int trace_max_ctas_per_sm(int service_threshold)
+int trace_max_ctas_per_sm()
 {
     int n = 0;
-    switch (service_threshold) {
-    case 8:  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<8>, kTraceThreads, 0); break;
-    case 16: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<16>, kTraceThreads, 0); break;
-    case 24: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<24>, kTraceThreads, 0); break;
-    case 32: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<32>, kTraceThreads, 0); break;
-    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<20>, kTraceThreads, 0); break;
-    }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace, kTraceThreads, 0);
     return n;
 }
 
@@ -800,6 +440,12 @@ cudaError_t launch_resolve(const FrameArgs& fa, int n_passes, int sampled, int w
 {
     const int threads = 256;
     k_resolve<<<(fa.geom.n_local + threads - 1) / threads, threads, 0, s>>>(fa, n_passes, sampled, write_display);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bn_prepare(void* bn, float2* table, int np, cudaStream_t s)
+{
+    k_bn_prepare<<<256, 256, 0, s>>>(reinterpret_cast<float3*>(bn), table, np);
     return cudaGetLastError();
 }
 

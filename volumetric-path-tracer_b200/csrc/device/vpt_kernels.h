@@ -7,7 +7,8 @@
 
 namespace vpt {
 
-constexpr int kTraceThreads = 256;
+constexpr int kTraceThreads = 128;
+constexpr int kTraceMinCtas = 4;     // __launch_bounds__ hint: <= 128 registers per thread
 
 // Which pixels this rank renders: rows are dealt to ranks in interleaved stripes of `stripe_h` rows
 // (rank r owns stripes r, r+R, r+2R, ...).  One rank: identity mapping, local == global indices.
@@ -26,8 +27,13 @@ struct FrameArgs {
     const vpt_sphere* sphere;
     const SceneTables* scene;
     FrameGeom         geom;
-    // ray queue (hits): 2 x float4 per record, plus its two counters
-    float4*   queue;
+    // ray queue (hits), SoA: direction + entry distance | (local pixel, pass | draws<<6 | obj<<16) | origin (thin lens only)
+    float4*   queue_dir;
+    uint2*    queue_id;
+    float4*   queue_org;           // null for a pinhole camera (origin == cam.origin)
+    const float2* bn_table;        // [pass][65536] blue-noise jitter of the chunk
+    int       debug_flags;         // development switches (0 in production)
+    int       sched_min_lanes;     // trace scheduler: lanes an operation must gather before it pre-empts stepping
     unsigned* queue_count;
     unsigned* queue_head;
     // sample planes, [pass][local pixel]
@@ -39,9 +45,10 @@ struct FrameArgs {
 cudaError_t launch_prepare_scene(const vpt_gpu_vdb* vols, const vpt_octnode* root, SceneTables* out, OctInternal* internal,
                                  uint2* leaf_list, int* leaf_indices, VolumeRec* vrec, int max_volumes, cudaStream_t s);
 cudaError_t launch_generate(const FrameArgs& fa, int n_passes, cudaStream_t s);
-cudaError_t launch_trace(const FrameArgs& fa, int n_ctas, int service_threshold, cudaStream_t s);
-int         trace_max_ctas_per_sm(int service_threshold);
+cudaError_t launch_trace(const FrameArgs& fa, int n_ctas, cudaStream_t s);
+int         trace_max_ctas_per_sm();
 cudaError_t launch_resolve(const FrameArgs& fa, int n_passes, int sampled, int write_display, cudaStream_t s);
+cudaError_t launch_bn_prepare(void* bn, float2* table, int np, cudaStream_t s);
 cudaError_t launch_bn_advance(void* bn, int n, cudaStream_t s);
 cudaError_t launch_unpermute(const void* gathered, void* full, const FrameGeom& g, int elem_bytes, cudaStream_t s);
 

@@ -32,10 +32,23 @@ VPT_DEV float3 operator/(float3 a, float s) { return make_float3(a.x / s, a.y / 
 VPT_DEV void operator+=(float3& a, float3 b) { a.x += b.x; a.y += b.y; a.z += b.z; }
 VPT_DEV void operator*=(float3& a, float3 b) { a.x *= b.x; a.y *= b.y; a.z *= b.z; }
 VPT_DEV void operator*=(float3& a, float s) { a.x *= s; a.y *= s; a.z *= s; }
-VPT_DEV float  dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// Pinned arithmetic.  nvcc's contraction of `a*b + c` into fma depends on the surrounding control flow (the same
+// source line compiled to mul+sub in one version of the trace kernel and to fma in another, which moved a handful
+// of samples by one texture-filter quantum).  Everything that feeds a tracking decision is therefore spelled with
+// explicit single-rounding intrinsics, in the operation order of the reference build's PTX:
+//   x*x + y*y + z*z  ->  fma(z, z, fma(x, x, y*y))      a*b - c*d  ->  mul, mul, sub (never fused)
+VPT_DEV float  pmul(float a, float b) { return __fmul_rn(a, b); }
+VPT_DEV float  padd(float a, float b) { return __fadd_rn(a, b); }
+VPT_DEV float  psub(float a, float b) { return __fsub_rn(a, b); }
+VPT_DEV float  pfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+VPT_DEV float  dot(float3 a, float3 b) { return pfma(a.z, b.z, pfma(a.x, b.x, pmul(a.y, b.y))); }
 VPT_DEV float  length(float3 v) { return sqrtf(dot(v, v)); }
-VPT_DEV float3 normalize(float3 v) { float inv = rsqrtf(dot(v, v)); return v * inv; }
-VPT_DEV float3 cross(float3 a, float3 b) { return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+VPT_DEV float3 normalize(float3 v) { float inv = rsqrtf(dot(v, v)); return make_float3(pmul(v.x, inv), pmul(v.y, inv), pmul(v.z, inv)); }
+VPT_DEV float3 cross(float3 a, float3 b) {
+    return make_float3(psub(pmul(a.y, b.z), pmul(a.z, b.y)), psub(pmul(a.z, b.x), pmul(a.x, b.z)), psub(pmul(a.x, b.y), pmul(a.y, b.x)));
+}
+// p + d * t with one rounding per component (fma), the form every position update of the reference compiles to
+VPT_DEV float3 madd3(float3 p, float3 d, float t) { return make_float3(pfma(d.x, t, p.x), pfma(d.y, t, p.y), pfma(d.z, t, p.z)); }
 VPT_DEV float3 lerp3(float3 a, float3 b, float t) { return a + t * (b - a); }
 VPT_DEV float3 reflect3(float3 i, float3 n) { return i - 2.0f * n * dot(n, i); }
 VPT_DEV float  clampf(float f, float a, float b) { return fmaxf(a, fminf(f, b)); }
@@ -65,7 +78,7 @@ VPT_DEV PhiloxBlock philox4x32_10(uint32_t c0, uint32_t c1, uint32_t key0) {
 }
 
 // curand_uniform: x * 2^-32 + 2^-33, in (0, 1]  (curand_uniform.h:69-72)
-VPT_DEV float u32_to_unit(uint32_t x) { return x * 2.3283064e-10f + (2.3283064e-10f / 2.0f); }
+VPT_DEV float u32_to_unit(uint32_t x) { return pfma((float)x, 2.3283064e-10f, 2.3283064e-10f / 2.0f); }
 
 struct Rng {
     uint32_t key;      // global pixel index

@@ -56,7 +56,7 @@ VPT_DEV bool solve_quadratic(float a, float b, float c, float& x1, float& x2) {
         x1 = 0; x2 = sqrtf(-c / a);
         return true;
     }
-    float discr = b * b - 4 * a * c;
+    float discr = pfma(b, b, pmul(pmul(a, -4.0f), c));         // b*b - 4*a*c as the reference build evaluates it
     if (discr < 0) return false;
     float q = (b < 0.f) ? -0.5f * (b - sqrtf(discr)) : -0.5f * (b + sqrtf(discr));
     x1 = q / a;
@@ -66,9 +66,10 @@ VPT_DEV bool solve_quadratic(float a, float b, float c, float& x1, float& x2) {
 
 VPT_DEV bool sphere_intersect(const SphereRec& s, float3 ray_pos, float3 ray_dir, float& t_min, float& t_max) {
     float3 orig = ray_pos - s.center;
-    float A = ray_dir.x * ray_dir.x + ray_dir.y * ray_dir.y + ray_dir.z * ray_dir.z;
-    float B = 2 * (ray_dir.x * orig.x + ray_dir.y * orig.y + ray_dir.z * orig.z);
-    float C = orig.x * orig.x + orig.y * orig.y + orig.z * orig.z - s.radius * s.radius;
+    float A = dot(ray_dir, ray_dir);
+    float Bh = dot(ray_dir, orig);
+    float B = padd(Bh, Bh);
+    float C = psub(dot(orig, orig), pmul(s.radius, s.radius));
     if (!solve_quadratic(A, B, C, t_min, t_max)) return false;
     if (t_min > t_max) { float tmp = t_max; t_max = t_min; t_min = tmp; }
     if (t_min < 0) {
@@ -126,21 +127,21 @@ VPT_DEV int oct_locate_or_skip(const OctShared& oct, const SceneTables& sc, floa
     const int c1 = oct_child(r, ray_pos);
     if ((r.child_empty >> c1) & 1u) {
         float t_max = fmaxf(oct_child_exit(r, c1, ray_pos, ray_dir), 0.1f);
-        ray_pos += ray_dir * t_max;
+        ray_pos = madd3(ray_pos, ray_dir, t_max);
         return -2;
     }
     const OctInternal& n1 = oct.node[1 + c1];
     const int c2 = oct_child(n1, ray_pos);
     if ((n1.child_empty >> c2) & 1u) {
         float t_max = fmaxf(oct_child_exit(n1, c2, ray_pos, ray_dir), 0.1f);
-        ray_pos += ray_dir * t_max;
+        ray_pos = madd3(ray_pos, ray_dir, t_max);
         return -2;
     }
     const OctInternal& n2 = oct.node[9 + c1 * 8 + c2];
     const int c3 = oct_child(n2, ray_pos);
     if ((n2.child_empty >> c3) & 1u) {
         float t_max = fmaxf(oct_child_exit(n2, c3, ray_pos, ray_dir), 0.1f);
-        ray_pos += ray_dir * t_max;
+        ray_pos = madd3(ray_pos, ray_dir, t_max);
         return -2;
     }
     return c1 * 64 + c2 * 8 + c3;
@@ -150,11 +151,12 @@ VPT_DEV int oct_locate_or_skip(const OctShared& oct, const SceneTables& sc, floa
 // world -> normalised texture coordinate; the operand order reproduces the reference's inlined
 // `xform.transpose().inverse().transform_point(pos)` followed by `(pos - bmin) / dim`.
 VPT_DEV bool volume_coord(const VolumeRec& v, float3 p, float3& uvw) {
-    float ix = p.x * v.m[0][0] + p.y * v.m[0][1] + p.z * v.m[0][2] + v.adj3[0] * v.idet;
-    float iy = p.x * v.m[1][0] + p.y * v.m[1][1] + p.z * v.m[1][2] + v.adj3[1] * v.idet;
-    float iz = p.x * v.m[2][0] + p.y * v.m[2][1] + p.z * v.m[2][2] + v.adj3[2] * v.idet;
-    ix -= v.bmin[0]; iy -= v.bmin[1]; iz -= v.bmin[2];
-    uvw.x = ix * v.rdim[0]; uvw.y = iy * v.rdim[1]; uvw.z = iz * v.rdim[2];
+    // mul(y), fma(x), fma(z), fma(adjugate, 1/det): the chain the reference's inlined inverse + transform_point compiles to
+    float ix = pfma(v.adj3[0], v.idet, pfma(p.z, v.m[0][2], pfma(p.x, v.m[0][0], pmul(p.y, v.m[0][1]))));
+    float iy = pfma(v.adj3[1], v.idet, pfma(p.z, v.m[1][2], pfma(p.x, v.m[1][0], pmul(p.y, v.m[1][1]))));
+    float iz = pfma(v.adj3[2], v.idet, pfma(p.z, v.m[2][2], pfma(p.x, v.m[2][0], pmul(p.y, v.m[2][1]))));
+    ix = psub(ix, v.bmin[0]); iy = psub(iy, v.bmin[1]); iz = psub(iz, v.bmin[2]);
+    uvw.x = pmul(ix, v.rdim[0]); uvw.y = pmul(iy, v.rdim[1]); uvw.z = pmul(iz, v.rdim[2]);   // div.approx == rcp.approx * x
     return !(uvw.x < .0f || uvw.y < .0f || uvw.z < .0f || uvw.x > 1.0f || uvw.y > 1.0f || uvw.z > 1.0f);
 }
 
@@ -182,24 +184,24 @@ VPT_DEV float3 volume_emission(const VolumeRec& v, float3 p, const float3* lut, 
     return lut[int(index)] * scale;
 }
 
-VPT_DEV float leaf_density(const SceneTables& sc, int leaf, float3 p) {
-    if (sc.single_volume) return 0.0f + volume_density(sc.volumes[0], p);
+VPT_DEV float leaf_density(const SceneTables& sc, const VolumeRec& vol0, int leaf, float3 p) {
+    if (sc.single_volume) return 0.0f + volume_density(vol0, p);
     const uint2 lst = sc.leaf_list[leaf];
     float density = 0.0f;
     for (uint32_t i = 0; i < lst.y; ++i) density += volume_density(sc.volumes[sc.leaf_indices[lst.x + i]], p);
     return density;
 }
 
-VPT_DEV float3 leaf_color(const SceneTables& sc, int leaf, float3 p) {
-    if (sc.single_volume) return fmax3(f3(0.0f), volume_color(sc.volumes[0], p));
+VPT_DEV float3 leaf_color(const SceneTables& sc, const VolumeRec& vol0, int leaf, float3 p) {
+    if (sc.single_volume) return fmax3(f3(0.0f), volume_color(vol0, p));
     const uint2 lst = sc.leaf_list[leaf];
     float3 color = f3(0.0f);
     for (uint32_t i = 0; i < lst.y; ++i) color = fmax3(color, volume_color(sc.volumes[sc.leaf_indices[lst.x + i]], p));
     return color;
 }
 
-VPT_DEV float3 leaf_emission(const SceneTables& sc, int leaf, float3 p, const float3* lut, float pivot, float scale) {
-    if (sc.single_volume) return f3(0.0f) + volume_emission(sc.volumes[0], p, lut, pivot, scale);
+VPT_DEV float3 leaf_emission(const SceneTables& sc, const VolumeRec& vol0, int leaf, float3 p, const float3* lut, float pivot, float scale) {
+    if (sc.single_volume) return f3(0.0f) + volume_emission(vol0, p, lut, pivot, scale);
     const uint2 lst = sc.leaf_list[leaf];
     float3 e = f3(0.0f);
     for (uint32_t i = 0; i < lst.y; ++i) e += volume_emission(sc.volumes[sc.leaf_indices[lst.x + i]], p, lut, pivot, scale);
@@ -214,20 +216,28 @@ VPT_DEV float hg_phase(float cos_theta, float g) {           // reference henyey
 
 VPT_DEV void hg_sample(float3& wo, Rng& rng, float g) {       // reference sample_hg, render_kernel.cu:306-325
     float cos_theta;
-    if (fabsf(g) < VPT_EPS) cos_theta = 1 - 2 * rng.next();
+    if (fabsf(g) < VPT_EPS) { const float u = rng.next(); cos_theta = psub(1.0f, padd(u, u)); }
     else {
-        float sqr_term = (1 - g * g) / (1 - g + 2 * g * rng.next());
-        cos_theta = (1 + g * g - sqr_term * sqr_term) / (2 * g);
+        const float g2 = padd(g, g);
+        const float sqr_term = psub(1.0f, pmul(g, g)) / pfma(g2, rng.next(), psub(1.0f, g));
+        cos_theta = psub(pfma(g, g, 1.0f), pmul(sqr_term, sqr_term)) / g2;
     }
-    float sin_theta = sqrtf(fmaxf(.0f, 1.0f - cos_theta * cos_theta));
-    float phi = (float)(2.0 * 3.14159265358979323846) * rng.next();
-    // orthonormal frame around -wo
-    float3 v1 = wo * -1.0f, v2, v3;
+    const float sin_theta = sqrtf(fmaxf(psub(1.0f, pmul(cos_theta, cos_theta)), .0f));
+    const float phi = pmul(rng.next(), (float)(2.0 * 3.14159265358979323846));
+    // orthonormal frame around -wo (reference coordinate_system, :92-102)
+    const float3 v1 = make_float3(-wo.x, -wo.y, -wo.z);
+    float3 v2;
     if (fabsf(v1.x) > fabsf(v1.y)) v2 = f3(-v1.z, 0.0f, v1.x);
     else                           v2 = f3(0.0f, v1.z, -v1.y);
     v2 = normalize(v2);
-    v3 = normalize(cross(v1, v2));
-    wo = v2 * sin_theta * cosf(phi) + v3 * sin_theta * sinf(phi) + wo * cos_theta;
+    const float3 v3 = normalize(cross(v1, v2));
+    // x*sin*cos(phi) + y*sin*sin(phi) + z*cos  ->  mul(y term), fma(x term), fma(z term)
+    const float cp = cosf(phi), sp = sinf(phi);
+    const float3 xs = make_float3(pmul(sin_theta, v2.x), pmul(sin_theta, v2.y), pmul(sin_theta, v2.z));
+    const float3 ys = make_float3(pmul(sin_theta, v3.x), pmul(sin_theta, v3.y), pmul(sin_theta, v3.z));
+    wo = make_float3(pfma(wo.x, cos_theta, pfma(xs.x, cp, pmul(sp, ys.x))),
+                     pfma(wo.y, cos_theta, pfma(xs.y, cp, pmul(sp, ys.y))),
+                     pfma(wo.z, cos_theta, pfma(xs.z, cp, pmul(sp, ys.z))));
 }
 
 VPT_DEV float3 sun_direction(float azimuth, float elevation) {  // reference degree_to_cartesian, :126-142

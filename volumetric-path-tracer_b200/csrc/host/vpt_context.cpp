@@ -37,7 +37,6 @@ struct vpt_context {
     std::string err;
     // options
     int passes_per_chunk = 8;
-    int service_threshold = 20;
     int ctas_per_sm = 0;
     // partition
     int rank = 0, n_ranks = 1, stripe_rows = 16;
@@ -51,6 +50,9 @@ struct vpt_context {
     // frame buffers
     size_t cap_samples = 0;           // n_local * chunk
     bool   cap_planeD = false;
+    uint2* d_queue_id = nullptr; float4* d_queue_org = nullptr; float2* d_bn_table = nullptr; int cap_chunk = 0;
+    int sched_min_lanes = 16;
+    int debug_flags = 0;
     float4 *d_queue = nullptr, *d_planeA = nullptr, *d_planeB = nullptr, *d_planeC = nullptr, *d_planeD = nullptr;
     unsigned* d_counters = nullptr;   // [0] queue_count, [1] queue_head
     // stats
@@ -130,6 +132,7 @@ void vpt_destroy(vpt_context* c) {
     cudaFree(c->d_scene); cudaFree(c->d_internal); cudaFree(c->d_leaf_list); cudaFree(c->d_leaf_indices); cudaFree(c->d_vrec);
     cudaFree(c->d_stats);
     for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    cudaFree(c->d_queue_id); cudaFree(c->d_queue_org); cudaFree(c->d_bn_table);
     cudaFree(c->d_counters); cudaFree(c->d_queue); cudaFree(c->d_planeA); cudaFree(c->d_planeB); cudaFree(c->d_planeC); cudaFree(c->d_planeD);
     delete c;
 }
@@ -138,8 +141,9 @@ int vpt_set_option(vpt_context* c, const char* key, int value) {
     if (!c || !key) return fail(c, VPT_ERR_INVALID, "vpt_set_option: null argument");
     const std::string k(key);
     if (k == "passes_per_chunk") { if (value < 1 || value > 64) return fail(c, VPT_ERR_INVALID, "passes_per_chunk must be 1..64"); c->passes_per_chunk = value; }
-    else if (k == "service_threshold") { if (value != 8 && value != 16 && value != 20 && value != 24 && value != 32) return fail(c, VPT_ERR_INVALID, "service_threshold must be one of 8,16,20,24,32"); c->service_threshold = value; }
     else if (k == "ctas_per_sm") { if (value < 0 || value > 8) return fail(c, VPT_ERR_INVALID, "ctas_per_sm must be 0..8"); c->ctas_per_sm = value; }
+    else if (k == "sched_min_lanes") { if (value < 1 || value > 32) return fail(c, VPT_ERR_INVALID, "sched_min_lanes must be 1..32"); c->sched_min_lanes = value; }
+    else if (k == "debug_flags") { c->debug_flags = value; }
     else if (k == "count_stats") { c->count_stats = value ? 1 : 0; }
     else if (k == "profile") { c->profile = value ? 1 : 0; }
     else return fail(c, VPT_ERR_INVALID, "unknown option " + k);
@@ -181,8 +185,12 @@ int vpt_get_stats(vpt_context* c, unsigned long long* launches, unsigned* last_q
 static int ensure_frame_buffers(vpt_context* c, size_t n_samples, bool need_planeD) {
     if (n_samples > c->cap_samples) {
         cudaFree(c->d_queue); cudaFree(c->d_planeA); cudaFree(c->d_planeB); cudaFree(c->d_planeC); cudaFree(c->d_planeD);
-        c->d_queue = c->d_planeA = c->d_planeB = c->d_planeC = c->d_planeD = nullptr; c->cap_samples = 0; c->cap_planeD = false;
-        VPT_CUDA(c, cudaMalloc(&c->d_queue, n_samples * 2 * sizeof(float4)));
+        cudaFree(c->d_queue_id); cudaFree(c->d_queue_org);
+        c->d_queue = c->d_planeA = c->d_planeB = c->d_planeC = c->d_planeD = c->d_queue_org = nullptr; c->d_queue_id = nullptr;
+        c->cap_samples = 0; c->cap_planeD = false;
+        VPT_CUDA(c, cudaMalloc(&c->d_queue, n_samples * sizeof(float4)));
+        VPT_CUDA(c, cudaMalloc(&c->d_queue_id, n_samples * sizeof(uint2)));
+        VPT_CUDA(c, cudaMalloc(&c->d_queue_org, n_samples * sizeof(float4)));
         VPT_CUDA(c, cudaMalloc(&c->d_planeA, n_samples * sizeof(float4)));
         VPT_CUDA(c, cudaMalloc(&c->d_planeB, n_samples * sizeof(float4)));
         VPT_CUDA(c, cudaMalloc(&c->d_planeC, n_samples * sizeof(float4)));
@@ -245,10 +253,17 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         int rc = ensure_frame_buffers(c, per_chunk, planeD);
         if (rc != VPT_OK) return rc;
     }
-    fa.queue = c->d_queue; fa.queue_count = c->d_counters; fa.queue_head = c->d_counters + 1;
+    if (c->cap_chunk < chunk) {
+        cudaFree(c->d_bn_table); c->d_bn_table = nullptr;
+        VPT_CUDA(c, cudaMalloc(&c->d_bn_table, sizeof(float2) * 65536 * (size_t)chunk));
+        c->cap_chunk = chunk;
+    }
+    fa.queue_dir = c->d_queue; fa.queue_id = c->d_queue_id; fa.queue_org = (fa.cam.lens_radius != 0.0f) ? c->d_queue_org : nullptr;
+    fa.bn_table = c->d_bn_table; fa.sched_min_lanes = c->sched_min_lanes; fa.debug_flags = c->debug_flags;
+    fa.queue_count = c->d_counters; fa.queue_head = c->d_counters + 1;
     fa.planeA = c->d_planeA; fa.planeB = c->d_planeB; fa.planeC = c->d_planeC; fa.planeD = planeD ? c->d_planeD : nullptr;
 
-    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : vpt::trace_max_ctas_per_sm(c->service_threshold);
+    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : vpt::trace_max_ctas_per_sm();
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int trace_ctas = c->num_sms * ctas_per_sm;
 
@@ -269,11 +284,11 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         const unsigned np = (n_sampled - done) < (unsigned)chunk ? (n_sampled - done) : (unsigned)chunk;
         fa.kp.iteration = it0 + done;
         VPT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned) * 2, stream));
-        VPT_CUDA(c, timed(0, [&] { return vpt::launch_generate(fa, (int)np, stream); }));   // reads the blue-noise state of pass `done`
-        VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, trace_ctas, c->service_threshold, stream); }));
+        VPT_CUDA(c, timed(3, [&] { return vpt::launch_bn_prepare((void*)kp.blue_noise_buffer, c->d_bn_table, (int)np, stream); }));   // jitter table + advance
+        VPT_CUDA(c, timed(0, [&] { return vpt::launch_generate(fa, (int)np, stream); }));
+        VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, trace_ctas, stream); }));
         const bool last = (done + np == n_passes);
         VPT_CUDA(c, timed(2, [&] { return vpt::launch_resolve(fa, (int)np, 1, last ? 1 : 0, stream); }));
-        VPT_CUDA(c, timed(3, [&] { return vpt::launch_bn_advance((void*)kp.blue_noise_buffer, (int)np, stream); }));
         c->launches += 4;
         done += np;
     }
