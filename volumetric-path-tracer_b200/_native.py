@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvpt_b200.so")
+LIB_PATH = os.path.join(_HERE, "lib", os.environ.get("VPT_LIB_NAME", "libvpt_b200.so"))   # VPT_LIB_NAME: tuning builds only
 
 
 class NativeLibraryMissing(ImportError):

@@ -423,16 +423,25 @@ cudaError_t launch_generate(const FrameArgs& fa, int n_passes, cudaStream_t s)
     return cudaGetLastError();
 }
 
+static size_t trace_smem_bytes() { return (size_t)kTraceWarps * kRayWords * kPool * sizeof(float); }
+
 cudaError_t launch_trace(const FrameArgs& fa, int n_ctas, cudaStream_t s)
 {
-    k_trace<<<n_ctas, kTraceThreads, 0, s>>>(fa);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k_trace<<<n_ctas, kTraceThreads, trace_smem_bytes(), s>>>(fa);
     return cudaGetLastError();
 }
 
 int trace_max_ctas_per_sm()
 {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace, kTraceThreads, 0);
+    cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace, kTraceThreads, trace_smem_bytes());
     return n;
 }
 

@@ -8,7 +8,10 @@
 namespace vpt {
 
 constexpr int kTraceThreads = 128;
-constexpr int kTraceMinCtas = 4;     // __launch_bounds__ hint: <= 128 registers per thread
+#ifndef VPT_TRACE_MIN_CTAS
+#define VPT_TRACE_MIN_CTAS 4
+#endif
+constexpr int kTraceMinCtas = VPT_TRACE_MIN_CTAS;     // __launch_bounds__ hint: 4 CTAs x (51 KB ray slots + 4 KB tables) and <= 128 registers per thread
 
 // Which pixels this rank renders: rows are dealt to ranks in interleaved stripes of `stripe_h` rows
 // (rank r owns stripes r, r+R, r+2R, ...).  One rank: identity mapping, local == global indices.

@@ -63,7 +63,8 @@ VPT_DEV bool   any_inf(float3 v) { return isinf(v.x) || isinf(v.y) || isinf(v.z)
 // counter = ((iteration*4096 mod 2^32) / 4, 0, 0, 0); draw k is lane (k & 3) of block (k >> 2).
 struct PhiloxBlock { uint32_t x, y, z, w; };
 
-VPT_DEV PhiloxBlock philox4x32_10(uint32_t c0, uint32_t c1, uint32_t key0) {
+// one out-of-line copy: ~60 integer instructions that would otherwise be inlined at every draw site
+__device__ __noinline__ PhiloxBlock philox4x32_10(uint32_t c0, uint32_t c1, uint32_t key0) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
     uint32_t x0 = c0, x1 = c1, x2 = 0u, x3 = 0u, k0 = key0, k1 = 0u;
 #pragma unroll

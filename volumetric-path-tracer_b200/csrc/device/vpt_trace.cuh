@@ -1,30 +1,37 @@
-// vpt_trace.cuh -- k_trace: persistent wavefront over the hit queue, scheduled per warp by operation.
+// vpt_trace.cuh -- k_trace: persistent wavefront over the hit queue, three rays per lane.
+// (included from vpt_kernels.cu inside `namespace vpt`)
 //
-// Every lane owns one ray and carries an `op` = the next heavy operation its path needs:
+// Divergence is the enemy of this path: a ray needs a different heavy operation every few hundred
+// instructions (closest-object test, tracking step, HG resampling, transmittance set-up, bookkeeping)
+// and walks have geometric length.  One-ray-per-lane designs measured 10-12 active lanes per issued
+// instruction (profiles/).  Here every LANE owns kSlots = 3 rays, parked in shared memory (34 words each,
+// word-major so that lane l only ever touches bank l: conflict-free, no inter-lane hand-over) and tagged,
+// in registers, with the operation they wait for:
+//
 //     OP_STEP     one unified tracking step (delta / residual-ratio / emission walk)
 //     OP_CLOSEST  nearest of {octree root box, sphere}            (reference get_closest_object)
 //     OP_HG       Henyey-Greenstein direction resampling          (reference sample_hg)
 //     OP_TRBEGIN  set-up of a residual-ratio transmittance walk   (reference Tr prologue)
-//     OP_FINISH   write the sample record
-//     OP_GLUE     cheap bookkeeping between the above (the integrator's control flow)
-// Each operation has exactly ONE code site.  Every round the warp votes (ballot + popc) and executes
-// the operation most lanes are waiting for, so divergent estimator code runs with a majority of the
-// lanes active instead of one lane at a time, and the kernel's instruction footprint stays small enough
-// for the instruction cache (the first version inlined the transitions: 15 k SASS instructions, 37 %
-// of stall samples were instruction-fetch misses, 10 of 32 lanes active on average -- profiles/).
-// Finished lanes refill from the ray queue with one atomic per warp.
+//     OP_GLUE     integrator bookkeeping after a walk ended       OP_IDLE  free slot
+//
+// Each round the warp votes (one ballot per operation: "does any of your rays want it?") and runs the ONE
+// code site most lanes can take part in; a lane joins with whichever of its rays carries that tag, runs
+// the integrator's control flow (`advance`) behind the operation and parks the ray again.  Stepping is a
+// loop: a lane whose walker finished swaps in another of its walkers, so the step body keeps most lanes
+// busy until the warp runs out of walkers.  Free slots are refilled from the global ray queue with one
+// atomic per warp.  Every heavy operation has a single code site, which also keeps the kernel inside the
+// instruction cache (the first, inlined version spent 37 % of its stall samples on instruction fetch).
 //
 // Control flow restated from the reference direct integrator (render_kernel.cu:1760-1857) with three
 // bit-exact shortcuts: (1) the depth pass replays the integrator's first walk on a copy of the RNG
 // (:1859-1889), so it is taken from that walk instead of being run again; (2) the closest-object test
 // at the end of a bounce and the one at the top of the next have identical inputs unless the sphere
-// branch ran, so the result is reused; (3) a bounce that finds nothing ahead makes every later bounce
-// a no-op, so the path retires there.
+// branch ran, so the result is reused (and the very first one comes from k_generate); (3) a bounce that
+// finds nothing ahead makes every later bounce a no-op, so the path retires there.
 #pragma once
-// (included from vpt_kernels.cu inside `namespace vpt`)
 
 enum WalkMode : int { W_DELTA = 1, W_RATIO = 2, W_EMIT = 3 };
-enum Op : int { OP_IDLE = 0, OP_GLUE, OP_STEP, OP_CLOSEST, OP_HG, OP_TRBEGIN, OP_FINISH };
+enum Op : int { OP_IDLE = 0, OP_GLUE, OP_STEP, OP_CLOSEST, OP_TRBEGIN, OP_FINISH };
 enum Phase : int {
     PH_BOUNCE_TOP = 0, PH_TOP_HAVE, PH_VOL_ITER, PH_AFTER_DELTA, PH_AFTER_HG, PH_VOL_DONE, PH_AFTER_TR,
     PH_POINT_NEXT, PH_EMISSION, PH_AFTER_EMIT, PH_AFTER_VOLUME, PH_AFTERVOL_HAVE, PH_SPHERE
@@ -32,10 +39,17 @@ enum Phase : int {
 enum ExitReason : int { EX_NONE = 0, EX_OUTSIDE, EX_DISTANCE, EX_SCATTER, EX_TR_DONE };
 enum TrKind : int { TR_SUN = 0, TR_POINT = 1, TR_SPHERE = 2 };
 
+#ifndef VPT_TRACE_SLOTS
+#define VPT_TRACE_SLOTS 3
+#endif
+constexpr int kSlots = VPT_TRACE_SLOTS;   // rays per lane (2 or 3)
+constexpr int kPool = 32 * kSlots;        // rays per warp
+constexpr int kRayWords = 34;             // 32-bit words per ray in shared memory
+constexpr int kTraceWarps = kTraceThreads / 32;
+
 struct PathState {
     float3 pos, dir;      // the integrator's ray
-    float3 org;           // camera-ray origin (depth reference, default env_pos)
-    float3 env_pos;
+    float3 org;           // camera-ray origin (depth reference, default env_pos); not stored: pinhole -> cam.origin, else queue_org[qslot]
     float3 beta, L;
     float  alpha;         // the reference's `tr` out-parameter (accumulated density, capped at 1 at the end)
     float  depth;
@@ -47,9 +61,9 @@ struct PathState {
     int    obj_c;
     int    op, phase, mode, exit_reason, tr_kind;
     int    rd, vd, light_budget, light_index;
-    bool   mi, first_walk, have_closest;
-    uint32_t lp, pass;
-    uint32_t nlook;
+    bool   mi, first_walk, have_closest, sphere_bounced;
+    bool   sphere_free;   // the running walk's line provably misses the sphere: its per-step intersection tests are skipped
+    uint32_t lp, pass, qslot;
     Rng    rng;
 };
 
@@ -58,8 +72,104 @@ struct TraceConsts {
     float3 sun_dir;
 };
 
-// ---- OP_STEP ---------------------------------------------------------------------------------------------
-VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph)
+// ---- ray record <-> registers ------------------------------------------------------------------------------
+// pool layout: word w of slot j of lane l at pool[w * kPool + j * 32 + l]  (bank == lane: conflict-free)
+struct PoolView {
+    float* w;                                                    // this warp's kRayWords * kPool words, already offset by the lane
+    VPT_DEV float& f(int word, int slot) const { return w[word * kPool + slot * 32]; }
+    VPT_DEV uint32_t& u(int word, int slot) const { return reinterpret_cast<uint32_t*>(w)[word * kPool + slot * 32]; }
+};
+
+VPT_DEV void store_ray(const PoolView& pv, int s, const PathState& st)
+{
+    pv.f(0, s) = st.pos.x;  pv.f(1, s) = st.pos.y;  pv.f(2, s) = st.pos.z;
+    pv.f(3, s) = st.dir.x;  pv.f(4, s) = st.dir.y;  pv.f(5, s) = st.dir.z;
+    pv.f(6, s) = st.L.x;    pv.f(7, s) = st.L.y;    pv.f(8, s) = st.L.z;
+    pv.f(9, s) = st.beta.x; pv.f(10, s) = st.beta.y; pv.f(11, s) = st.beta.z;
+    pv.f(12, s) = st.wpos.x; pv.f(13, s) = st.wpos.y; pv.f(14, s) = st.wpos.z;
+    pv.f(15, s) = st.wdir.x; pv.f(16, s) = st.wdir.y; pv.f(17, s) = st.wdir.z;
+    pv.f(18, s) = st.aux.x; pv.f(19, s) = st.aux.y; pv.f(20, s) = st.aux.z;
+    pv.f(21, s) = st.alpha; pv.f(22, s) = st.depth; pv.f(23, s) = st.t; pv.f(24, s) = st.distance;
+    pv.f(25, s) = st.trv;   pv.f(26, s) = st.T_c;   pv.f(27, s) = st.tmin_c;
+    pv.u(28, s) = st.rng.k; pv.u(29, s) = st.lp;
+    pv.u(30, s) = (uint32_t)st.phase | ((uint32_t)st.mode << 4) | ((uint32_t)st.exit_reason << 6) | ((uint32_t)st.tr_kind << 9) |
+                  ((uint32_t)st.obj_c << 11) | ((uint32_t)st.mi << 13) | ((uint32_t)st.first_walk << 14) | ((uint32_t)st.have_closest << 15) |
+                  ((uint32_t)st.sphere_bounced << 16) | ((uint32_t)st.sphere_free << 17) | (st.pass << 18);
+    pv.u(31, s) = (uint32_t)(st.rd & 0xffff) | ((uint32_t)(st.vd & 0xffff) << 16);
+    pv.u(32, s) = (uint32_t)(st.light_budget & 0xff) | ((uint32_t)st.light_index << 8);
+    pv.u(33, s) = st.qslot;
+}
+
+VPT_DEV void ray_rng_init(PathState& st, const FrameArgs& fa, uint32_t k)
+{
+    uint32_t idx = st.lp;
+    const FrameGeom& g = fa.geom;
+    if (g.n_ranks > 1) {
+        const uint32_t lr = st.lp / (uint32_t)g.width, x = st.lp - lr * (uint32_t)g.width;
+        idx = (uint32_t)global_row(g, (int)lr) * (uint32_t)g.width + x;
+    }
+    st.rng.init(idx, fa.kp.iteration + st.pass, k);
+}
+
+VPT_DEV void load_ray(const PoolView& pv, int s, PathState& st, const FrameArgs& fa)
+{
+    st.pos = f3(pv.f(0, s), pv.f(1, s), pv.f(2, s));    st.dir = f3(pv.f(3, s), pv.f(4, s), pv.f(5, s));
+    st.L = f3(pv.f(6, s), pv.f(7, s), pv.f(8, s));      st.beta = f3(pv.f(9, s), pv.f(10, s), pv.f(11, s));
+    st.wpos = f3(pv.f(12, s), pv.f(13, s), pv.f(14, s)); st.wdir = f3(pv.f(15, s), pv.f(16, s), pv.f(17, s));
+    st.aux = f3(pv.f(18, s), pv.f(19, s), pv.f(20, s));
+    st.alpha = pv.f(21, s); st.depth = pv.f(22, s); st.t = pv.f(23, s); st.distance = pv.f(24, s);
+    st.trv = pv.f(25, s);   st.T_c = pv.f(26, s);   st.tmin_c = pv.f(27, s);
+    const uint32_t k = pv.u(28, s); st.lp = pv.u(29, s);
+    const uint32_t a = pv.u(30, s), b = pv.u(31, s), c = pv.u(32, s);
+    st.phase = a & 15; st.mode = (a >> 4) & 3; st.exit_reason = (a >> 6) & 7; st.tr_kind = (a >> 9) & 3; st.obj_c = (a >> 11) & 3;
+    st.mi = (a >> 13) & 1; st.first_walk = (a >> 14) & 1; st.have_closest = (a >> 15) & 1; st.sphere_bounced = (a >> 16) & 1; st.sphere_free = (a >> 17) & 1; st.pass = a >> 18;
+    st.rd = b & 0xffff; st.vd = b >> 16;
+    st.light_budget = (int)(int8_t)(c & 0xff); st.light_index = c >> 8;
+    st.qslot = pv.u(33, s);
+    st.org = fa.queue_org ? f3(__ldg(fa.queue_org + st.qslot).x, __ldg(fa.queue_org + st.qslot).y, __ldg(fa.queue_org + st.qslot).z) : ld3(fa.cam.origin);
+    ray_rng_init(st, fa, k);
+}
+
+// A walk only touches part of the record: 19 words in, 15 words out instead of 34 each way.
+VPT_DEV void load_walk(const PoolView& pv, int s, PathState& st, const FrameArgs& fa)
+{
+    st.beta = f3(pv.f(9, s), pv.f(10, s), pv.f(11, s));
+    st.wpos = f3(pv.f(12, s), pv.f(13, s), pv.f(14, s)); st.wdir = f3(pv.f(15, s), pv.f(16, s), pv.f(17, s));
+    st.aux = f3(pv.f(18, s), pv.f(19, s), pv.f(20, s));
+    st.alpha = pv.f(21, s); st.t = pv.f(23, s); st.distance = pv.f(24, s); st.trv = pv.f(25, s);
+    const uint32_t k = pv.u(28, s); st.lp = pv.u(29, s);
+    const uint32_t a = pv.u(30, s);
+    st.phase = a & 15; st.mode = (a >> 4) & 3; st.exit_reason = (a >> 6) & 7; st.tr_kind = (a >> 9) & 3; st.obj_c = (a >> 11) & 3;
+    st.mi = (a >> 13) & 1; st.first_walk = (a >> 14) & 1; st.have_closest = (a >> 15) & 1; st.sphere_bounced = (a >> 16) & 1; st.sphere_free = (a >> 17) & 1; st.pass = a >> 18;
+    ray_rng_init(st, fa, k);
+}
+
+VPT_DEV void store_walk(const PoolView& pv, int s, const PathState& st)
+{
+    pv.f(9, s) = st.beta.x; pv.f(10, s) = st.beta.y; pv.f(11, s) = st.beta.z;
+    pv.f(12, s) = st.wpos.x; pv.f(13, s) = st.wpos.y; pv.f(14, s) = st.wpos.z;
+    pv.f(18, s) = st.aux.x; pv.f(19, s) = st.aux.y; pv.f(20, s) = st.aux.z;
+    pv.f(21, s) = st.alpha; pv.f(23, s) = st.t; pv.f(24, s) = st.distance; pv.f(25, s) = st.trv;
+    pv.u(28, s) = st.rng.k;
+    pv.u(30, s) = (uint32_t)st.phase | ((uint32_t)st.mode << 4) | ((uint32_t)st.exit_reason << 6) | ((uint32_t)st.tr_kind << 9) |
+                  ((uint32_t)st.obj_c << 11) | ((uint32_t)st.mi << 13) | ((uint32_t)st.first_walk << 14) | ((uint32_t)st.have_closest << 15) |
+                  ((uint32_t)st.sphere_bounced << 16) | ((uint32_t)st.sphere_free << 17) | (st.pass << 18);
+}
+
+// Conservative test: true only if the infinite line p + s*d stays clear of the sphere enlarged by a margin three orders
+// of magnitude above float rounding (2e-3 of |c-p|^2 plus 2 % of r^2).  Then every sphere::intersect the reference
+// evaluates along this line returns "no hit" whatever the rounding, so those tests (and whatever only they could
+// trigger) are skipped; lines that come anywhere near the sphere take the exact path.
+VPT_DEV bool line_misses_sphere(const SphereRec& s, float3 p, float3 d)
+{
+    const float3 oc = s.center - p;
+    const float oc2 = oc.x * oc.x + oc.y * oc.y + oc.z * oc.z, dd = d.x * d.x + d.y * d.y + d.z * d.z, b = oc.x * d.x + oc.y * d.y + oc.z * d.z;
+    const float dist2 = oc2 - b * b / dd;
+    return dist2 > 1.02f * s.radius * s.radius + 2e-3f * oc2 + 1e-6f;
+}
+
+// ---- OP_STEP -------------------------------------------------------------------------------------------------
+VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph, uint32_t& nlook)
 {
     const SceneTables& sc = fs.sc;
     const vpt_kernel_params& kp = fa.kp;
@@ -71,7 +181,7 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
         // distance to the box exit (or to the sphere) from the CURRENT position, every step (:1647-1651)
         float t_min, t_max, geo_dist = .0f;
         aabb_intersect(sc.root_pmin, sc.root_pmax, st.wpos, st.wdir, t_min, st.distance);
-        if (sphere_intersect(sph, st.wpos, st.wdir, geo_dist, t_max)) st.distance = geo_dist;
+        if (!st.sphere_free && sphere_intersect(sph, st.wpos, st.wdir, geo_dist, t_max)) st.distance = geo_dist;
     }
     const float u = st.rng.next();
     // t -= log(1-u) * a * b, as the reference build evaluates it: fma(b, a * (lg2(1-u) * -ln2), t)
@@ -84,7 +194,7 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
     st.wpos = madd3(st.wpos, st.wdir, st.t);                  // cumulative t, never reset (quirk Q2)
     if (!aabb_contains(sc.root_pmin, sc.root_pmax, st.wpos)) { st.op = OP_GLUE; st.exit_reason = EX_OUTSIDE; return; }
 
-    st.nlook++;
+    nlook++;
     if (st.mode == W_EMIT) {
         st.aux += leaf_emission(sc, fs.vol0, leaf, st.wpos, reinterpret_cast<const float3*>(kp.emission_texture), kp.emission_pivot, kp.emission_scale);
         return;
@@ -105,7 +215,7 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
     }
 }
 
-// ---- OP_TRBEGIN: reference Tr prologue (:1150-1167); the walk starts from (st.wpos, st.wdir) -------------
+// ---- OP_TRBEGIN: reference Tr prologue (:1150-1167); the walk starts from (st.wpos, st.wdir) -----------------
 VPT_DEV void begin_ratio_walk(PathState& st, const FrameShared& fs, const TraceConsts& tc, const SphereRec& sph)
 {
     const SceneTables& sc = fs.sc;
@@ -118,7 +228,8 @@ VPT_DEV void begin_ratio_walk(PathState& st, const FrameShared& fs, const TraceC
         else { st.trv = 1.0f; return; }                         // misses the volume box: transmittance 1
     }
     aabb_intersect(sc.root_pmin, sc.root_pmax, p, d, t_min, distance);
-    if (sphere_intersect(sph, p, d, geo_dist, t_max)) { st.trv = 0.0f; return; }   // sphere occludes: BLACK
+    st.sphere_free = line_misses_sphere(sph, p, d);
+    if (!st.sphere_free && sphere_intersect(sph, p, d, geo_dist, t_max)) { st.trv = 0.0f; return; }   // sphere occludes: BLACK
     st.T_c = expf(-tc.sigma_c * distance);
     st.wpos = p; st.t = 0.0f; st.distance = distance; st.trv = 1.0f;
     st.mode = W_RATIO; st.op = OP_STEP;
@@ -126,7 +237,7 @@ VPT_DEV void begin_ratio_walk(PathState& st, const FrameShared& fs, const TraceC
 
 VPT_DEV float finish_ratio_walk(const PathState& st) { return clampf(st.trv * st.T_c, .0f, 1.0f); }
 
-// ---- OP_GLUE: the integrator's control flow between heavy operations -------------------------------------
+// ---- the integrator's control flow between heavy operations -------------------------------------------------
 VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph)
 {
     const SceneTables& sc = fs.sc;
@@ -156,9 +267,13 @@ VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, 
             if (st.vd > kp.volume_depth) { st.phase = PH_VOL_DONE; break; }
             st.mi = false;
             st.wpos = st.pos; st.wdir = st.dir;
-            st.phase = PH_AFTER_DELTA;
-            if (!(fa.debug_flags & 2) && !aabb_contains(sc.root_pmin, sc.root_pmax, st.pos)) { st.exit_reason = EX_OUTSIDE; break; }   // walk would leave at once
-            st.t = 0.0f; st.distance = .0f; st.mode = W_DELTA; st.op = OP_STEP;
+            if (!aabb_contains(sc.root_pmin, sc.root_pmax, st.pos)) {
+                // `sample` leaves at once, and so does every remaining volume_depth iteration (ray unchanged, no draw)
+                st.exit_reason = EX_OUTSIDE; st.vd = kp.volume_depth; st.phase = PH_AFTER_DELTA;
+                break;
+            }
+            st.sphere_free = line_misses_sphere(sph, st.pos, st.dir);
+            st.t = 0.0f; st.distance = .0f; st.mode = W_DELTA; st.op = OP_STEP; st.phase = PH_AFTER_DELTA;
             return;
         case PH_AFTER_DELTA: {
             st.pos = st.wpos;                                       // `sample` advances the caller's ray_pos
@@ -173,7 +288,7 @@ VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, 
                 st.first_walk = false;
             }
             if (is_black(st.beta) || obj == 2) { st.phase = PH_VOL_DONE; break; }
-            if (st.mi) { st.op = OP_HG; st.phase = PH_AFTER_HG; return; }
+            if (st.mi) hg_sample(st.dir, st.rng, kp.phase_g1);
             st.vd++; st.phase = PH_VOL_ITER;
             break;
         }
@@ -212,7 +327,8 @@ VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, 
                 st.phase = PH_POINT_NEXT;
             } else {                                                // sphere branch tail (:1831-1833)
                 st.L += ld3(kp.sun_color) * kp.sun_mult * f3(tr) * fmaxf(dot(tc.sun_dir, st.aux), .0f) * st.beta;
-                st.env_pos = st.pos;
+                if (fa.planeD) fa.planeD[(size_t)st.pass * fa.geom.n_local + st.lp] = make_float4(st.pos.x, st.pos.y, st.pos.z, 0.f);   // env_pos = ray_pos
+                st.sphere_bounced = true;
                 st.rd++; st.have_closest = false;
                 st.phase = PH_BOUNCE_TOP;
             }
@@ -238,13 +354,21 @@ VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, 
             st.L += st.aux;
             st.phase = PH_AFTER_VOLUME;
             break;
-        case PH_AFTER_VOLUME:                                       // the ray moved since the last test
+        case PH_AFTER_VOLUME: {                                     // the ray moved since the last test
+            // Later bounces cannot change the sample unless the sphere comes into play (quirk Q21: a ray inside the box is
+            // teleported to its exit, a ray outside it and leaving sees nothing).  If this ray's line provably misses the
+            // sphere and the position is not exactly on the box boundary, retire the path here: bit-identical output.
+            const bool inside_strict = st.pos.x > sc.root_pmin[0] && st.pos.x < sc.root_pmax[0] && st.pos.y > sc.root_pmin[1] &&
+                                       st.pos.y < sc.root_pmax[1] && st.pos.z > sc.root_pmin[2] && st.pos.z < sc.root_pmax[2];
+            const bool outside = !aabb_contains(sc.root_pmin, sc.root_pmax, st.pos);
+            // outside here means the walk stepped out of the box along dir (or never re-entered it): the box lies behind
+            if ((inside_strict || (outside && st.exit_reason == EX_OUTSIDE && !st.sphere_bounced)) && line_misses_sphere(sph, st.pos, st.dir)) { st.op = OP_FINISH; return; }
             st.op = OP_CLOSEST; st.phase = PH_AFTERVOL_HAVE;
             return;
+        }
         case PH_AFTERVOL_HAVE:
             if (st.obj_c == 2) { st.phase = PH_SPHERE; break; }
             st.rd++; st.phase = PH_BOUNCE_TOP;                      // next bounce starts from the same ray: reuse the test
-            if (fa.debug_flags & 4) st.have_closest = false;
             break;
         case PH_SPHERE: {                                           // bounce off the reference sphere (:1807-1834)
             st.pos += st.dir * st.tmin_c;
@@ -273,15 +397,25 @@ VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, 
     }
 }
 
+VPT_DEV void write_sample(const PathState& st, const FrameArgs& fa)
+{
+    const size_t o = (size_t)st.pass * fa.geom.n_local + st.lp;
+    fa.planeA[o] = make_float4(st.dir.x, st.dir.y, st.dir.z, st.alpha);                 // final direction, tr
+    fa.planeB[o] = make_float4(st.L.x, st.L.y, st.L.z, st.depth);                       // L, depth
+    fa.planeC[o] = make_float4(st.beta.x, st.beta.y, st.beta.z, 1.f);                   // beta
+    if (fa.planeD && !st.sphere_bounced) fa.planeD[o] = make_float4(st.org.x, st.org.y, st.org.z, 0.f);   // env_pos = camera origin unless the sphere branch moved it
+}
+
 __global__ void __launch_bounds__(kTraceThreads, kTraceMinCtas)
 k_trace(const FrameArgs fa)
 {
     __shared__ FrameShared fs;
+    extern __shared__ float pool_smem[];                         // kTraceWarps x kRayWords x kPool words (opt-in dynamic shared memory)
     load_frame_shared(fs, fa.scene);
     const SceneTables& sc = fs.sc;
     const vpt_kernel_params& kp = fa.kp;
-    const FrameGeom& g = fa.geom;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     TraceConsts tc;
     tc.inv_max = 1.0f / sc.max_extinction;
@@ -291,90 +425,111 @@ k_trace(const FrameArgs fa)
     tc.sun_dir = sun_direction(kp.azimuth, kp.elevation);
     const SphereRec sph = load_sphere(fa.sphere);
 
+    PoolView pv; pv.w = pool_smem + (size_t)warp * kRayWords * kPool + lane;
+    constexpr int OP_NOSLOT = 15;                                 // third slot disabled when kSlots == 2
+    int tag0 = OP_IDLE, tag1 = OP_IDLE, tag2 = (kSlots > 2) ? OP_IDLE : OP_NOSLOT;   // operation each of my rays waits for
+
     const unsigned q_count = *fa.queue_count;
-    PathState st;
-    st.op = OP_IDLE; st.nlook = 0;
     bool queue_dry = (q_count == 0);
-    uint32_t lane_steps = 0, warp_iters = 0, lane_ops = 0, warp_ops = 0;   // statistics
+    uint32_t nlook = 0, lane_steps = 0, warp_iters = 0, lane_ops = 0, warp_ops = 0;   // statistics
+    PathState st;
 
     for (;;) {
-        // ---- retire finished paths (three coalescible stores) ----
-        if (__ballot_sync(0xffffffffu, st.op == OP_FINISH)) {
-            if (st.op == OP_FINISH) {
-                const size_t s = (size_t)st.pass * g.n_local + st.lp;
-                fa.planeA[s] = make_float4(st.dir.x, st.dir.y, st.dir.z, st.alpha);
-                fa.planeB[s] = make_float4(st.L.x, st.L.y, st.L.z, st.depth);
-                fa.planeC[s] = make_float4(st.beta.x, st.beta.y, st.beta.z, 1.f);
-                if (fa.planeD) fa.planeD[s] = make_float4(st.env_pos.x, st.env_pos.y, st.env_pos.z, 0.f);
-                st.op = OP_IDLE;
-            }
-        }
-        // ---- refill idle lanes from the ray queue: one atomic per warp, amortised over >= 8 lanes ----
-        const unsigned idle = __ballot_sync(0xffffffffu, st.op == OP_IDLE);
-        if (idle == 0xffffffffu && queue_dry) break;
-        if (idle && !queue_dry && (__popc(idle) >= kRefillLanes || idle == 0xffffffffu ||
-                                   __ballot_sync(0xffffffffu, st.op == OP_STEP) == 0u)) {
+        // ---- refill free slots from the global queue: one atomic per warp, one record per lane that has room ----------
+        const bool has_idle = (tag0 == OP_IDLE) | (tag1 == OP_IDLE) | (tag2 == OP_IDLE);
+        const unsigned idle_lanes = __ballot_sync(0xffffffffu, has_idle);
+        if (!queue_dry && __popc(idle_lanes) >= fa.sched_min_lanes) {
             unsigned base = 0;
-            const int leader = __ffs(idle) - 1;
-            if (lane == leader) base = atomicAdd(fa.queue_head, __popc(idle));
+            const int leader = __ffs(idle_lanes) - 1;
+            if (lane == leader) base = atomicAdd(fa.queue_head, (unsigned)__popc(idle_lanes));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (base + __popc(idle) >= q_count) queue_dry = true;
-            if (st.op == OP_IDLE) {
-                const unsigned slot = base + __popc(idle & ((1u << lane) - 1u));
-                if (slot < q_count) {
-                    const float4 r0 = __ldg(fa.queue_dir + slot);
-                    const uint2 id = __ldg(fa.queue_id + slot);
-                    st.dir = f3(r0.x, r0.y, r0.z);
-                    st.org = fa.queue_org ? f3(__ldg(fa.queue_org + slot).x, __ldg(fa.queue_org + slot).y, __ldg(fa.queue_org + slot).z) : ld3(fa.cam.origin);
-                    st.lp = id.x;
-                    st.pass = id.y & 63u;
-                    uint32_t idx = st.lp;
-                    if (g.n_ranks > 1) {
-                        const uint32_t lr = st.lp / (uint32_t)g.width, x = st.lp - lr * (uint32_t)g.width;
-                        idx = (uint32_t)global_row(g, (int)lr) * (uint32_t)g.width + x;
-                    }
-                    st.rng.init(idx, kp.iteration + st.pass, (id.y >> 6) & 1023u);
-                    st.pos = st.org; st.env_pos = st.org;
-                    st.beta = f3(1.0f); st.L = f3(.0f); st.alpha = .0f; st.depth = .0f;
-                    st.mi = false; st.first_walk = true; st.rd = 1;
-                    st.tmin_c = r0.w; st.obj_c = (int)(id.y >> 16); st.have_closest = !(fa.debug_flags & 1);   // k_generate already ran the first test
-                    st.op = OP_GLUE; st.phase = PH_BOUNCE_TOP;
-                }
+            if (base + __popc(idle_lanes) >= q_count) queue_dry = true;
+            const unsigned slot = base + __popc(idle_lanes & lt_mask);
+            if (has_idle && slot < q_count) {
+                const int j = (tag0 == OP_IDLE) ? 0 : (tag1 == OP_IDLE) ? 1 : 2;
+                const float4 r0 = __ldg(fa.queue_dir + slot);
+                const uint2 id = __ldg(fa.queue_id + slot);
+                st.dir = f3(r0.x, r0.y, r0.z);
+                st.qslot = slot;
+                st.org = fa.queue_org ? f3(__ldg(fa.queue_org + slot).x, __ldg(fa.queue_org + slot).y, __ldg(fa.queue_org + slot).z) : ld3(fa.cam.origin);
+                st.lp = id.x; st.pass = id.y & 63u;
+                st.rng.k = (id.y >> 6) & 1023u;
+                st.pos = st.org;
+                st.beta = f3(1.0f); st.L = f3(.0f); st.alpha = .0f; st.depth = .0f;
+                st.wpos = st.pos; st.wdir = st.dir; st.aux = f3(0.f); st.t = 0.f; st.distance = 0.f; st.trv = 1.f; st.T_c = 1.f;
+                st.mi = false; st.first_walk = true; st.sphere_bounced = false; st.rd = 1; st.vd = 1; st.light_budget = 0; st.light_index = 0;
+                st.mode = W_DELTA; st.exit_reason = EX_NONE; st.tr_kind = TR_SUN;
+                st.tmin_c = r0.w; st.obj_c = (int)(id.y >> 16); st.have_closest = true;       // k_generate already ran the first test
+                st.phase = PH_BOUNCE_TOP; st.sphere_free = false; st.op = OP_GLUE;
+                store_ray(pv, j, st);
+                if (j == 0) tag0 = OP_GLUE; else if (j == 1) tag1 = OP_GLUE; else tag2 = OP_GLUE;
             }
         }
-        // ---- bookkeeping for lanes between heavy operations ----
-        if (st.op == OP_GLUE) advance(st, fs, fa, tc, sph);
 
-        // ---- vote: one operation per round.  Operations other than STEP run once per lane and unblock walkers, so
-        //      the largest such group runs as soon as it has gathered `sched_min_lanes` lanes (or nobody is stepping);
-        //      otherwise every walker takes one step.
-        const unsigned mS = __ballot_sync(0xffffffffu, st.op == OP_STEP);
-        const unsigned mC = __ballot_sync(0xffffffffu, st.op == OP_CLOSEST);
-        const unsigned mH = __ballot_sync(0xffffffffu, st.op == OP_HG);
-        const unsigned mT = __ballot_sync(0xffffffffu, st.op == OP_TRBEGIN);
-        const int nS = __popc(mS), nC = __popc(mC), nH = __popc(mH), nT = __popc(mT);
-        if ((nS | nC | nH | nT) == 0) continue;                 // only finishes / refills pending
-        const int others = max(nC, max(nH, nT));
-        if (nS > 0 && (others < fa.sched_min_lanes && !(others > 0 && nS < others))) {
-            if (st.op == OP_STEP) { walk_step(st, fs, fa, tc, sph); lane_steps++; }
-            warp_iters++;
-        } else if (nC >= nH && nC >= nT) {
-            if (st.op == OP_CLOSEST) {
-                st.obj_c = closest_object(sc, sph, st.pos, st.dir, st.tmin_c);
-                st.have_closest = true; st.op = OP_GLUE; lane_ops++;
+        // ---- vote: step, or service the rays that wait for bookkeeping / a closest-object test / a transmittance set-up? ----
+        const bool has_step = (tag0 == OP_STEP) | (tag1 == OP_STEP) | (tag2 == OP_STEP);
+        const bool svc0 = (tag0 != OP_STEP) & (tag0 != OP_IDLE), svc1 = (tag1 != OP_STEP) & (tag1 != OP_IDLE), svc2 = (tag2 != OP_STEP) & (tag2 != OP_IDLE) & (tag2 != OP_NOSLOT);
+        const int nS = __popc(__ballot_sync(0xffffffffu, has_step));
+        const int nV = __popc(__ballot_sync(0xffffffffu, svc0 | svc1 | svc2));
+        if ((nS | nV) == 0) {
+            if (queue_dry) break;                                  // nothing parked, nothing left to fetch
+            continue;                                              // everything idle: the refill above takes records next round
+        }
+
+        if (nV > nS) {
+            // ---- service round: one parked ray per participating lane runs [closest-object test] -> integrator control flow
+            //      (incl. HG resampling, NEE bookkeeping, retirement) -> [transmittance set-up]; each block has one code site ----
+            const int j = svc0 ? 0 : svc1 ? 1 : svc2 ? 2 : -1;
+            if (j >= 0) {
+                load_ray(pv, j, st, fa);
+                st.op = (j == 0) ? tag0 : (j == 1) ? tag1 : tag2;
+                if (st.op == OP_CLOSEST) {
+                    st.obj_c = closest_object(sc, sph, st.pos, st.dir, st.tmin_c);
+                    st.have_closest = true; st.op = OP_GLUE;
+                }
+                if (st.op == OP_GLUE) advance(st, fs, fa, tc, sph);
+                if (st.op == OP_TRBEGIN) begin_ratio_walk(st, fs, tc, sph);
+                if (st.op == OP_FINISH) { write_sample(st, fa); st.op = OP_IDLE; }
+                else store_ray(pv, j, st);
+                if (j == 0) tag0 = st.op; else if (j == 1) tag1 = st.op; else tag2 = st.op;
+                lane_ops++;
             }
             warp_ops++;
-        } else if (nT >= nH) {
-            if (st.op == OP_TRBEGIN) { begin_ratio_walk(st, fs, tc, sph); lane_ops++; }
-            warp_ops++;
-        } else {
-            if (st.op == OP_HG) { hg_sample(st.dir, st.rng, kp.phase_g1); st.op = OP_GLUE; lane_ops++; }
-            warp_ops++;
+            continue;
+        }
+
+        // ---- stepping loop: a lane steps one of its walkers; when that walk ends it parks the ray and swaps in its next walker ----
+        {
+            int cur = -1;
+            int parked_lanes = nV;                                // lanes with something to service (grows as walks end)
+            for (;;) {
+                if (cur < 0) {
+                    cur = (tag0 == OP_STEP) ? 0 : (tag1 == OP_STEP) ? 1 : (tag2 == OP_STEP) ? 2 : -1;
+                    if (cur >= 0) { load_walk(pv, cur, st, fa); st.op = OP_STEP; }
+                }
+                const unsigned walking = __ballot_sync(0xffffffffu, cur >= 0);
+                if (walking == 0u) break;
+                // few walkers left and a fuller group is waiting: park and let the vote pick it
+                if (__popc(walking) < fa.sched_min_lanes && parked_lanes > __popc(walking)) {
+                    if (cur >= 0) { store_walk(pv, cur, st); cur = -1; }
+                    break;
+                }
+                if (cur >= 0) {
+                    walk_step(st, fs, fa, tc, sph, nlook); lane_steps++;
+                    if (st.op != OP_STEP) {                        // walk ended: park the ray with its new tag
+                        store_walk(pv, cur, st);
+                        if (cur == 0) tag0 = st.op; else if (cur == 1) tag1 = st.op; else tag2 = st.op;
+                        cur = -1;
+                    }
+                }
+                parked_lanes = __popc(__ballot_sync(0xffffffffu, ((tag0 != OP_STEP) & (tag0 != OP_IDLE)) | ((tag1 != OP_STEP) & (tag1 != OP_IDLE)) | ((tag2 != OP_STEP) & (tag2 != OP_IDLE) & (tag2 != OP_NOSLOT))));
+                warp_iters++;
+            }
         }
     }
 
     if (fa.counters) {                                        // optional statistics (one atomic set per warp)
-        unsigned long long a = st.nlook, b = lane_steps, c = lane_ops;
+        unsigned long long a = nlook, b = lane_steps, c = lane_ops;
         for (int o = 16; o > 0; o >>= 1) {
             a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o);
         }
@@ -384,4 +539,3 @@ k_trace(const FrameArgs fa)
         }
     }
 }
-
