@@ -5,7 +5,7 @@ run() { echo "=== $*"; timeout 300 python tools/gpu_compare.py "$@" 2>&1 | grep 
 run 256 256 2 ray_depth=3 volume_depth=3
 run 640 360 3 ray_depth=100
 echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-for L in 4 8 16; do
+for L in 8 16; do
 echo "== bench ours sched_min_lanes=$L"; timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --sched-min-lanes $L 2>&1 | tail -1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.read()); r = d['roofline']

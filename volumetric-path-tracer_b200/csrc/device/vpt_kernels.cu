@@ -202,6 +202,7 @@ k_generate(const FrameArgs fa)
     float3 org = f3(0.f), dir = f3(0.f, 0.f, 1.f);
     uint32_t kdraws = 0;
     int obj = 0; float t_min = 0.f;
+    bool prestepped = false; float3 wstart = f3(0.f);
     const uint32_t lp = (uint32_t)lr * (uint32_t)g.width + (uint32_t)x;
 
     if (valid) {
@@ -238,6 +239,21 @@ k_generate(const FrameArgs fa)
         obj = closest_object(sc, sph, org, dir, t_min);
         hit = (obj != 0);
 
+        // Draw-free prefix of the first delta walk: until the ray reaches a non-empty octree leaf the reference's `sample`
+        // only hops over empty nodes (no random number is consumed).  Run those hops here, at full warp width; a ray that
+        // leaves the box without ever meeting a populated leaf contributes exactly what a miss does and never enters the
+        // queue, the others are queued at the position where stepping really starts.  (Pinhole camera and a ray whose line
+        // provably misses the sphere only; everything else takes the generic route.)
+        if (obj == 1 && kp.ray_depth >= 1 && kp.volume_depth >= 1 && cam.lens_radius == 0.0f && line_misses_sphere(sph, org, dir)) {
+            float3 p = madd3(org, dir, padd(t_min, VPT_EPS));
+            int leaf = -2;
+            if (!aabb_contains(sc.root_pmin, sc.root_pmax, p)) leaf = -1;
+            for (int it = 0; it < 256 && leaf == -2; ++it) leaf = oct_locate_or_skip(fs.oct, sc, p, dir);
+            if (leaf == -1) hit = false;                         // walked out through empty space: sample == miss sample
+            else if (leaf >= 0) { prestepped = true; wstart = p; }
+            // leaf == -2 after 256 hops: leave it to the generic route
+        }
+
         if (!hit) {
             const size_t s = (size_t)pass * g.n_local + lp;
             fa.planeA[s] = make_float4(dir.x, dir.y, dir.z, 0.0f);     // final direction, tr
@@ -257,8 +273,9 @@ k_generate(const FrameArgs fa)
             // 24-byte record (+16 B origin when the lens is not a pinhole): direction + entry distance, ids + RNG position
             const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
             fa.queue_dir[slot] = make_float4(dir.x, dir.y, dir.z, t_min);
-            fa.queue_id[slot] = make_uint2(lp, (uint32_t)pass | (kdraws << 6) | ((uint32_t)obj << 16));
-            if (fa.queue_org) fa.queue_org[slot] = make_float4(org.x, org.y, org.z, 0.f);
+            fa.queue_id[slot] = make_uint2(lp, (uint32_t)pass | (kdraws << 6) | ((uint32_t)obj << 16) | ((uint32_t)prestepped << 18));
+            if (prestepped) fa.queue_aux[slot] = make_float4(wstart.x, wstart.y, wstart.z, 0.f);      // where stepping starts
+            else if (fa.thin_lens) fa.queue_aux[slot] = make_float4(org.x, org.y, org.z, 0.f);   // thin lens: per-ray origin
         }
     }
 }

@@ -33,7 +33,8 @@ struct FrameArgs {
     // ray queue (hits), SoA: direction + entry distance | (local pixel, pass | draws<<6 | obj<<16) | origin (thin lens only)
     float4*   queue_dir;
     uint2*    queue_id;
-    float4*   queue_org;           // null for a pinhole camera (origin == cam.origin)
+    float4*   queue_aux;           // thin lens: per-ray origin; pre-stepped ray (pinhole only): position where stepping starts
+    int       thin_lens;           // cam.lens_radius != 0
     const float2* bn_table;        // [pass][65536] blue-noise jitter of the chunk
     int       debug_flags;         // development switches (0 in production)
     int       sched_min_lanes;     // trace scheduler: lanes an operation must gather before it pre-empts stepping

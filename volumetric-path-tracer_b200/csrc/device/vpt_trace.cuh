@@ -126,7 +126,7 @@ VPT_DEV void load_ray(const PoolView& pv, int s, PathState& st, const FrameArgs&
     st.rd = b & 0xffff; st.vd = b >> 16;
     st.light_budget = (int)(int8_t)(c & 0xff); st.light_index = c >> 8;
     st.qslot = pv.u(33, s);
-    st.org = fa.queue_org ? f3(__ldg(fa.queue_org + st.qslot).x, __ldg(fa.queue_org + st.qslot).y, __ldg(fa.queue_org + st.qslot).z) : ld3(fa.cam.origin);
+    st.org = fa.thin_lens ? f3(__ldg(fa.queue_aux + st.qslot).x, __ldg(fa.queue_aux + st.qslot).y, __ldg(fa.queue_aux + st.qslot).z) : ld3(fa.cam.origin);
     ray_rng_init(st, fa, k);
 }
 
@@ -156,25 +156,14 @@ VPT_DEV void store_walk(const PoolView& pv, int s, const PathState& st)
                   ((uint32_t)st.sphere_bounced << 16) | ((uint32_t)st.sphere_free << 17) | (st.pass << 18);
 }
 
-// Conservative test: true only if the infinite line p + s*d stays clear of the sphere enlarged by a margin three orders
-// of magnitude above float rounding (2e-3 of |c-p|^2 plus 2 % of r^2).  Then every sphere::intersect the reference
-// evaluates along this line returns "no hit" whatever the rounding, so those tests (and whatever only they could
-// trigger) are skipped; lines that come anywhere near the sphere take the exact path.
-VPT_DEV bool line_misses_sphere(const SphereRec& s, float3 p, float3 d)
-{
-    const float3 oc = s.center - p;
-    const float oc2 = oc.x * oc.x + oc.y * oc.y + oc.z * oc.z, dd = d.x * d.x + d.y * d.y + d.z * d.z, b = oc.x * d.x + oc.y * d.y + oc.z * d.z;
-    const float dist2 = oc2 - b * b / dd;
-    return dist2 > 1.02f * s.radius * s.radius + 2e-3f * oc2 + 1e-6f;
-}
-
 // ---- OP_STEP -------------------------------------------------------------------------------------------------
 VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph, uint32_t& nlook)
 {
     const SceneTables& sc = fs.sc;
     const vpt_kernel_params& kp = fa.kp;
-    const int leaf = oct_locate_or_skip(fs.oct, sc, st.wpos, st.wdir);
-    if (leaf == -2) return;                                   // skipped an empty node, no draw consumed
+    int leaf = oct_locate_or_skip(fs.oct, sc, st.wpos, st.wdir);
+    if (leaf == -2) leaf = oct_locate_or_skip(fs.oct, sc, st.wpos, st.wdir);   // hop over up to two empty nodes per call (no draw consumed)
+    if (leaf == -2) return;
     if (leaf == -1) { st.op = OP_GLUE; st.exit_reason = EX_OUTSIDE; return; }
 
     if (st.mode == W_DELTA) {
@@ -451,7 +440,7 @@ k_trace(const FrameArgs fa)
                 const uint2 id = __ldg(fa.queue_id + slot);
                 st.dir = f3(r0.x, r0.y, r0.z);
                 st.qslot = slot;
-                st.org = fa.queue_org ? f3(__ldg(fa.queue_org + slot).x, __ldg(fa.queue_org + slot).y, __ldg(fa.queue_org + slot).z) : ld3(fa.cam.origin);
+                st.org = fa.thin_lens ? f3(__ldg(fa.queue_aux + slot).x, __ldg(fa.queue_aux + slot).y, __ldg(fa.queue_aux + slot).z) : ld3(fa.cam.origin);
                 st.lp = id.x; st.pass = id.y & 63u;
                 st.rng.k = (id.y >> 6) & 1023u;
                 st.pos = st.org;
@@ -459,10 +448,17 @@ k_trace(const FrameArgs fa)
                 st.wpos = st.pos; st.wdir = st.dir; st.aux = f3(0.f); st.t = 0.f; st.distance = 0.f; st.trv = 1.f; st.T_c = 1.f;
                 st.mi = false; st.first_walk = true; st.sphere_bounced = false; st.rd = 1; st.vd = 1; st.light_budget = 0; st.light_index = 0;
                 st.mode = W_DELTA; st.exit_reason = EX_NONE; st.tr_kind = TR_SUN;
-                st.tmin_c = r0.w; st.obj_c = (int)(id.y >> 16); st.have_closest = true;       // k_generate already ran the first test
+                st.tmin_c = r0.w; st.obj_c = (int)((id.y >> 16) & 3u); st.have_closest = true;       // k_generate already ran the first test
                 st.phase = PH_BOUNCE_TOP; st.sphere_free = false; st.op = OP_GLUE;
+                if ((id.y >> 18) & 1u) {
+                    // k_generate already hopped over the empty nodes in front of this ray: it is a delta walker at `wpos`
+                    const float4 ws = __ldg(fa.queue_aux + slot);
+                    st.wpos = f3(ws.x, ws.y, ws.z); st.pos = st.wpos;
+                    st.have_closest = false; st.sphere_free = true;
+                    st.phase = PH_AFTER_DELTA; st.op = OP_STEP;
+                }
                 store_ray(pv, j, st);
-                if (j == 0) tag0 = OP_GLUE; else if (j == 1) tag1 = OP_GLUE; else tag2 = OP_GLUE;
+                if (j == 0) tag0 = st.op; else if (j == 1) tag1 = st.op; else tag2 = st.op;
             }
         }
 

@@ -79,6 +79,18 @@ VPT_DEV bool sphere_intersect(const SphereRec& s, float3 ray_pos, float3 ray_dir
     return true;
 }
 
+// Conservative test: true only if the infinite line p + s*d stays clear of the sphere enlarged by a margin three orders
+// of magnitude above float rounding (2e-3 of |c-p|^2 plus 2 % of r^2).  Then every sphere::intersect the reference
+// evaluates along this line returns "no hit" whatever the rounding, so those tests (and whatever only they could
+// trigger) are skipped; lines that come anywhere near the sphere take the exact path.
+VPT_DEV bool line_misses_sphere(const SphereRec& s, float3 p, float3 d)
+{
+    const float3 oc = s.center - p;
+    const float oc2 = oc.x * oc.x + oc.y * oc.y + oc.z * oc.z, dd = d.x * d.x + d.y * d.y + d.z * d.z, b = oc.x * d.x + oc.y * d.y + oc.z * d.z;
+    const float dist2 = oc2 - b * b / dd;
+    return dist2 > 1.02f * s.radius * s.radius + 2e-3f * oc2 + 1e-6f;
+}
+
 // Nearest of {octree root box, reference sphere}: 1 = volume box, 2 = sphere, 0 = neither
 // (reference get_closest_object, render_kernel.cu:1118-1135).
 VPT_DEV int closest_object(const SceneTables& sc, const SphereRec& sph, float3 ray_pos, float3 ray_dir, float& t_min) {

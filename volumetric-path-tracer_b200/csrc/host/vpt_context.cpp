@@ -258,7 +258,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         VPT_CUDA(c, cudaMalloc(&c->d_bn_table, sizeof(float2) * 65536 * (size_t)chunk));
         c->cap_chunk = chunk;
     }
-    fa.queue_dir = c->d_queue; fa.queue_id = c->d_queue_id; fa.queue_org = (fa.cam.lens_radius != 0.0f) ? c->d_queue_org : nullptr;
+    fa.queue_dir = c->d_queue; fa.queue_id = c->d_queue_id; fa.queue_aux = c->d_queue_org; fa.thin_lens = (fa.cam.lens_radius != 0.0f) ? 1 : 0;
     fa.bn_table = c->d_bn_table; fa.sched_min_lanes = c->sched_min_lanes; fa.debug_flags = c->debug_flags;
     fa.queue_count = c->d_counters; fa.queue_head = c->d_counters + 1;
     fa.planeA = c->d_planeA; fa.planeB = c->d_planeB; fa.planeC = c->d_planeC; fa.planeD = planeD ? c->d_planeD : nullptr;
