@@ -260,7 +260,7 @@ def main():
         cpu_base = cpu_baseline_sample(V, scene, r.cam, kp)
 
     if rank == 0:
-        config.update({"passes_per_chunk": opts.get("passes_per_chunk", 8), "partition": f"{world} rank(s), interleaved 8-row stripes" if world > 1 else "single GPU",
+        config.update({"passes_per_chunk": opts.get("passes_per_chunk", 16), "partition": f"{world} rank(s), interleaved 8-row stripes" if world > 1 else "single GPU",
                        "collective": "1 NCCL all_gather_into_tensor of float3 accumulators per step" if world > 1 else "none"})
         line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",

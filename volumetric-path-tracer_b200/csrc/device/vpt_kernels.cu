@@ -19,7 +19,7 @@
 
 namespace vpt {
 
-constexpr int kRefillLanes = 8;      // idle lanes that justify the queue atomic
+constexpr uint32_t kMissSentinel = 0xffffffffu;   // planeA.w bit pattern marking a miss sample (a NaN no arithmetic produces)
 
 // =====================================================================================================
 // k_prepare_scene
@@ -187,6 +187,12 @@ __global__ void __launch_bounds__(128)
 k_generate(const FrameArgs fa)
 {
     __shared__ FrameShared fs;
+    __shared__ float vdc2[101], vdc3[101];                     // radical inverses of 0..100 in bases 2 and 3
+    // the lens sampler only ever asks for vanDerCorput(int(xi * 100)): tabulate it with the reference's own loop
+    if (threadIdx.x < 101) {
+        { int n = threadIdx.x; float r = 0, denom = 1, inv = 1.f / 2; while (n) { denom *= 2; r = padd(r, __fdividef((float)(n % 2), denom)); n *= inv; } vdc2[threadIdx.x] = r; }
+        { int n = threadIdx.x; float r = 0, denom = 1, inv = 1.f / 3; while (n) { denom *= 3; r = padd(r, __fdividef((float)(n % 3), denom)); n *= inv; } vdc3[threadIdx.x] = r; }
+    }
     load_frame_shared(fs, fa.scene);
     const SceneTables& sc = fs.sc;
     const FrameGeom& g = fa.geom;
@@ -194,10 +200,12 @@ k_generate(const FrameArgs fa)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 32 + warp * 8 + (lane & 7);
     const int lr = blockIdx.y * 4 + (lane >> 3);
-    const int pass = blockIdx.z;                                 // pass within this chunk
     const int y = global_row(g, lr);
     const bool valid = (x < g.width) && (lr < g.local_rows) && (y < g.height);
 
+    const SphereRec sph = load_sphere(fa.sphere);
+    // one block = one 32x4 pixel tile, all passes of the chunk (amortises the octree / table staging above)
+    for (int pass = 0; pass < fa.n_passes; ++pass) {
     bool hit = false;
     float3 org = f3(0.f), dir = f3(0.f, 0.f, 1.f);
     uint32_t kdraws = 0;
@@ -221,8 +229,8 @@ k_generate(const FrameArgs fa)
         // thin-lens ray (reference camera::get_ray, camera.h:131-136)
         float3 p;
         do {
-            const float a = van_der_corput<2>(rng);
-            const float b = van_der_corput<3>(rng);
+            const float a = vdc2[int(rng.next() * 100)];
+            const float b = vdc3[int(rng.next() * 100)];
             p = f3(pfma(a, 2.0f, -1.0f), pfma(b, 2.0f, -1.0f), 0.0f);
         } while (pfma(p.x, p.x, pmul(p.y, p.y)) >= 1.0f);
         const float3 rd = f3(pmul(cam.lens_radius, p.x), pmul(cam.lens_radius, p.y), 0.0f);
@@ -235,8 +243,9 @@ k_generate(const FrameArgs fa)
         dir = normalize(b);
         kdraws = rng.k;
 
-        const SphereRec sph = load_sphere(fa.sphere);
-        obj = closest_object(sc, sph, org, dir, t_min);
+        const bool sphere_clear = line_misses_sphere(sph, org, dir);   // then sphere::intersect is known to fail: skip it
+        if (sphere_clear) { float tmax1; obj = aabb_intersect(sc.root_pmin, sc.root_pmax, org, dir, t_min, tmax1) ? 1 : 0; }
+        else obj = closest_object(sc, sph, org, dir, t_min);
         hit = (obj != 0);
 
         // Draw-free prefix of the first delta walk: until the ray reaches a non-empty octree leaf the reference's `sample`
@@ -244,7 +253,7 @@ k_generate(const FrameArgs fa)
         // leaves the box without ever meeting a populated leaf contributes exactly what a miss does and never enters the
         // queue, the others are queued at the position where stepping really starts.  (Pinhole camera and a ray whose line
         // provably misses the sphere only; everything else takes the generic route.)
-        if (obj == 1 && kp.ray_depth >= 1 && kp.volume_depth >= 1 && cam.lens_radius == 0.0f && line_misses_sphere(sph, org, dir)) {
+        if (obj == 1 && kp.ray_depth >= 1 && kp.volume_depth >= 1 && cam.lens_radius == 0.0f && sphere_clear) {
             float3 p = madd3(org, dir, padd(t_min, VPT_EPS));
             int leaf = -2;
             if (!aabb_contains(sc.root_pmin, sc.root_pmax, p)) leaf = -1;
@@ -256,9 +265,8 @@ k_generate(const FrameArgs fa)
 
         if (!hit) {
             const size_t s = (size_t)pass * g.n_local + lp;
-            fa.planeA[s] = make_float4(dir.x, dir.y, dir.z, 0.0f);     // final direction, tr
-            fa.planeB[s] = make_float4(0.f, 0.f, 0.f, 0.f);           // L, depth
-            fa.planeC[s] = make_float4(1.f, 1.f, 1.f, 0.f);           // beta
+            // 16-byte miss record: direction + sentinel (L = 0, beta = 1, depth = 0, tr = 0 are implied; planes B/C untouched)
+            fa.planeA[s] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(kMissSentinel));
             if (fa.planeD) fa.planeD[s] = make_float4(org.x, org.y, org.z, 0.f);
         }
     }
@@ -278,6 +286,7 @@ k_generate(const FrameArgs fa)
             else if (fa.thin_lens) fa.queue_aux[slot] = make_float4(org.x, org.y, org.z, 0.f);   // thin lens: per-ray origin
         }
     }
+    }   // pass loop
 }
 
 #include "vpt_trace.cuh"
@@ -323,11 +332,14 @@ k_resolve(const FrameArgs fa, const int n_passes, const int sampled, const int w
         tr = .0f;
         if (sampled) {
             const size_t s = (size_t)p * g.n_local + lp;
-            const float4 A = fa.planeA[s], B = fa.planeB[s], C = fa.planeC[s];
-            const float3 ray_dir = f3(A.x, A.y, A.z), beta = f3(C.x, C.y, C.z);
-            float3 L = f3(B.x, B.y, B.z);
-            depth = B.w;
-            tr = A.w;
+            const float4 A = fa.planeA[s];
+            const float3 ray_dir = f3(A.x, A.y, A.z);
+            float3 beta = f3(1.0f), L = f3(0.0f);
+            if (__float_as_uint(A.w) != kMissSentinel) {          // hit sample: the trace kernel wrote all three planes
+                const float4 B = fa.planeB[s], C = fa.planeC[s];
+                beta = f3(C.x, C.y, C.z); L = f3(B.x, B.y, B.z);
+                depth = B.w; tr = A.w;
+            }
             if (kp.environment_type == 0) {
                 // Bruneton sky (reference sample_atmosphere): not part of this build yet; the host API
                 // refuses environment_type == 0, so this branch is never taken.
@@ -435,8 +447,9 @@ cudaError_t launch_prepare_scene(const vpt_gpu_vdb* vols, const vpt_octnode* roo
 
 cudaError_t launch_generate(const FrameArgs& fa, int n_passes, cudaStream_t s)
 {
-    dim3 grid((fa.geom.width + 31) / 32, (fa.geom.local_rows + 3) / 4, n_passes);
-    k_generate<<<grid, 128, 0, s>>>(fa);
+    dim3 grid((fa.geom.width + 31) / 32, (fa.geom.local_rows + 3) / 4, 1);
+    FrameArgs a = fa; a.n_passes = n_passes;
+    k_generate<<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -36,6 +36,7 @@ struct FrameArgs {
     float4*   queue_aux;           // thin lens: per-ray origin; pre-stepped ray (pinhole only): position where stepping starts
     int       thin_lens;           // cam.lens_radius != 0
     const float2* bn_table;        // [pass][65536] blue-noise jitter of the chunk
+    int       n_passes;            // passes in this chunk (k_generate loops over them)
     int       debug_flags;         // development switches (0 in production)
     int       sched_min_lanes;     // trace scheduler: lanes an operation must gather before it pre-empts stepping
     unsigned* queue_count;
