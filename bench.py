@@ -43,57 +43,67 @@ def workload_params(V):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  The sampler is started before the
+    warm-up (nvidia-smi needs ~1 s to start) and samples are kept by timestamp inside the timed window."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu = gpu_index; self.proc = None; self.lines = []
+        self.gpu = gpu_index; self.proc = None; self.lines = []; self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True); self.t.start()
+            time.sleep(1.5)
         except Exception:
             self.proc = None
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try: self.proc.wait(timeout=2)
         except Exception: self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9: continue
-            try:
-                sm.append(float(f[1])); smax = float(f[2])
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"): reasons.add(name)
-        busy = [x for x in sm if smax and x > 0.3 * smax] or sm
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        def parse(lines):
+            sm, smax, reasons = [], None, set()
+            for _, ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9: continue
+                try:
+                    sm.append(float(f[1])); smax = float(f[2])
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"): reasons.add(name)
+            return sm, smax, reasons
+        inside = [x for x in self.lines if self.t0 is not None and self.t0 - 0.02 <= x[0] <= self.t1 + 0.05]
+        sm, smax, reasons = parse(inside if inside else self.lines[-10:])
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "window_s": None if self.t0 is None else round(self.t1 - self.t0, 4)}
 
 
 def flush_l2(buf):
     buf.add_(1)      # 256 MiB read+write > 126 MB L2
 
 
-def timed_steps(step_fn, steps, warmup, dist, flush_buf):
+def timed_steps(step_fn, steps, warmup, dist, flush_buf, sampler=None):
     for _ in range(warmup):
         step_fn()
     torch.cuda.synchronize()
     if dist is not None: dist.barrier()
     torch.cuda.synchronize()
     evs = []
-    wall0 = time.perf_counter()
+    wall0 = time.perf_counter(); tw0 = time.time()
     for _ in range(steps):
         flush_l2(flush_buf)
         a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
@@ -103,6 +113,7 @@ def timed_steps(step_fn, steps, warmup, dist, flush_buf):
     if dist is not None: dist.barrier()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
+    if sampler is not None: sampler.window(tw0, time.time())
     ms = sum(a.elapsed_time(b) for a, b in evs)
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -167,7 +178,7 @@ def main():
                 orc.launch(r.params.array, WIDTH, HEIGHT, orc.UNMODIFIED, sync=True)
                 r.kp.iteration += 1
         sampler.start()
-        ms, wall = timed_steps(step, args.steps, args.warmup, None, flush_buf)
+        ms, wall = timed_steps(step, args.steps, args.warmup, None, flush_buf, sampler)
         clocks = sampler.stop()
         val = samples_per_step * args.steps / (ms * 1e-3) / 1e6
         config.update({"launch_protocol": "reference main loop: 1 launch + cudaDeviceSynchronize per spp, grid (W/16+1,H/16+1)x(16,16)",
@@ -203,7 +214,7 @@ def main():
 
     l0, _ = r.stats()
     sampler.start()
-    ms, wall = timed_steps(step, args.steps, args.warmup, dist, flush_buf)
+    ms, wall = timed_steps(step, args.steps, args.warmup, dist, flush_buf, sampler)
     clocks = sampler.stop()
     l1, _ = r.stats()
     launches_per_step = (l1 - l0) // (args.steps + args.warmup)
@@ -240,20 +251,33 @@ def main():
         for _ in range(2): step()
         kt = r.kernel_times(); cnt = r.counters()
         r.set_option("profile", 0); r.set_option("count_stats", 0)
-        n_local_samples = r.n_local * SPP * 2
-        lookups_per_sample = cnt["lookups"] / max(1, n_local_samples)
-        t_trace = kt["trace"]["ms"] / max(1, kt["trace"]["launches"])
-        samples_per_launch = n_local_samples / max(1, kt["trace"]["launches"])
-        bytes_per_sample = 88.0 + 32.0 * lookups_per_sample          # SURVEY 8(d): framebuffer stream + 32 B per density lookup
-        achieved = samples_per_launch * bytes_per_sample / (t_trace * 1e-3) / 1e9
+        n_steps_prof = 2
+        samples = r.n_local * SPP * n_steps_prof
+        launches = max(1, kt["trace"]["launches"])
+        t_trace = kt["trace"]["ms"] / launches
+        lookups_per_sample = cnt["lookups"] / max(1, samples)
+        # k_trace's own algorithmic bytes: 32 B per density lookup + per traced ray a 24-B queue record
+        # (+16 B start position) read and a 48-B sample record written
+        bytes_trace = 32.0 * cnt["lookups"] + (24.0 + 16.0 + 48.0) * cnt["rays"]
+        achieved = bytes_trace / launches / (t_trace * 1e-3) / 1e9
         simt = cnt["lane_steps"] / max(1, 32 * cnt["warp_step_iters"])
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("passes_per_launch") == opts.get("passes_per_chunk", 16) and world == 1: traffic = tj["k_trace_dram_bytes_per_launch"]
+        bytes_per_sample = 88.0 + 32.0 * lookups_per_sample          # SURVEY 8(d): framebuffer stream + 32 B per density lookup
+        step_gbs = value * bytes_per_sample / 1e3
         roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "bytes_per_sample": bytes_per_sample,
-                    "density_lookups_per_sample": lookups_per_sample, "samples_per_launch": samples_per_launch,
-                    "avg_launch_ms": t_trace, "step_loop_simt_efficiency": simt, "trace_counters": cnt,
-                    "kernel_ms_per_step": {k: v["ms"] / 2 for k, v in kt.items()},
-                    "note": "dragon.vdb is 425 KB: L2/TEX resident, so the HBM fraction is small by construction (SURVEY 8(d)); "
-                            "the path is latency/ALU bound, see profiles/"}
+                    "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": bytes_trace / launches, "avg_launch_ms": t_trace, "launches_per_step": launches / n_steps_prof,
+                    "density_lookups_per_sample": lookups_per_sample, "rays_traced_per_sample": cnt["rays"] / max(1, samples),
+                    "step_loop_simt_efficiency": simt, "service_round_lanes": cnt["lane_services"] / max(1, cnt["warp_service_rounds"]),
+                    "kernel_ms_per_step": {k: v["ms"] / n_steps_prof for k, v in kt.items()},
+                    "step": {"bytes_per_sample": bytes_per_sample, "achieved": step_gbs, "frac": step_gbs / peak,
+                             "note": "whole step charged with SURVEY 8(d)'s 88 B + 32 B x lookups per sample"},
+                    "note": "dragon.vdb is 425 KB: volume lookups are served by L1/TEX/L2, DRAM only sees the ray queue and the sample planes; "
+                            "the path is bound by latency / instruction issue, not HBM (SURVEY 8(d)); see profiles/"}
 
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:

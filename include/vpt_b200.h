@@ -81,8 +81,8 @@ int  vpt_invalidate_scene(vpt_context* ctx);
 int  vpt_get_stats(vpt_context* ctx, unsigned long long* kernel_launches_total, unsigned* last_queue_count);
 
 /* Instrumentation.  Option "count_stats" = 1 makes the trace kernel accumulate out[0] volume lookups,
- * out[1] lane-steps, out[2] warp step-loop iterations, out[3] lane transitions, out[4] warp transition rounds
- * (SIMT efficiency of the step loop = out[1] / (32 * out[2])).  Option "profile" = 1 brackets every kernel with
+ * out[1] lane-steps, out[2] warp step-loop iterations, out[3] rays serviced, out[4] warp service rounds, out[5] rays
+ * fetched from the queue (SIMT efficiency of the step loop = out[1] / (32 * out[2])).  Option "profile" = 1 brackets every kernel with
  * CUDA events: ms/n[0..3] = generate, trace, resolve, blue-noise advance.  Both calls synchronise the device. */
 int  vpt_get_counters(vpt_context* ctx, unsigned long long out[8], int reset);
 int  vpt_get_kernel_times(vpt_context* ctx, float ms[4], int n[4]);

@@ -420,7 +420,7 @@ k_trace(const FrameArgs fa)
 
     const unsigned q_count = *fa.queue_count;
     bool queue_dry = (q_count == 0);
-    uint32_t nlook = 0, lane_steps = 0, warp_iters = 0, lane_ops = 0, warp_ops = 0;   // statistics
+    uint32_t nlook = 0, lane_steps = 0, warp_iters = 0, lane_ops = 0, warp_ops = 0, lane_rays = 0;   // statistics
     PathState st;
 
     for (;;) {
@@ -459,6 +459,7 @@ k_trace(const FrameArgs fa)
                 }
                 store_ray(pv, j, st);
                 if (j == 0) tag0 = st.op; else if (j == 1) tag1 = st.op; else tag2 = st.op;
+                lane_rays++;
             }
         }
 
@@ -525,13 +526,13 @@ k_trace(const FrameArgs fa)
     }
 
     if (fa.counters) {                                        // optional statistics (one atomic set per warp)
-        unsigned long long a = nlook, b = lane_steps, c = lane_ops;
+        unsigned long long a = nlook, b = lane_steps, c = lane_ops, d = lane_rays;
         for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o);
+            a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o); d += __shfl_xor_sync(0xffffffffu, d, o);
         }
         if (lane == 0) {
             atomicAdd(fa.counters + 0, a); atomicAdd(fa.counters + 1, b); atomicAdd(fa.counters + 2, (unsigned long long)warp_iters);
-            atomicAdd(fa.counters + 3, c); atomicAdd(fa.counters + 4, (unsigned long long)warp_ops);
+            atomicAdd(fa.counters + 3, c); atomicAdd(fa.counters + 4, (unsigned long long)warp_ops); atomicAdd(fa.counters + 5, d);
         }
     }
 }

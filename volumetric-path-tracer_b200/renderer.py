@@ -105,7 +105,7 @@ class Renderer:
         out = (C.c_ulonglong * 8)()
         check(lib.vpt_get_counters(self.ctx, out, 1 if reset else 0), self.ctx, "vpt_get_counters")
         v = list(out)
-        return dict(lookups=v[0], lane_steps=v[1], warp_step_iters=v[2], lane_transitions=v[3], warp_transition_rounds=v[4])
+        return dict(lookups=v[0], lane_steps=v[1], warp_step_iters=v[2], lane_services=v[3], warp_service_rounds=v[4], rays=v[5])
 
     def kernel_times(self):
         ms = (C.c_float * 4)(); n = (C.c_int * 4)()
