@@ -159,6 +159,63 @@ def test_instance_transform_matches_reference_mat4_algebra(dragon):
         assert np.array_equal(np.array(list(out), dtype=np.float32).reshape(4, 4), instance_xform(base, pos, q, s))
 
 
+def _big_asset(name):
+    return V.find_asset(name)
+
+
+@needs_ref
+@pytest.mark.skipif(_big_asset("fireball.vdb") is None, reason="fireball.vdb not staged (oracle/_ref/assets)")
+def test_fireball_emission_against_reference():
+    """BASELINE config 3 parameters at reduced size: emission walk + blackbody LUT, heat grid addressed with the
+    density grid's bounds (quirk Q8), sigma_max = 12.47, multiple scattering through volume_depth."""
+    vol = V.Volume.load_vdb(_big_asset("fireball.vdb"))
+    assert vol.rec.vdb_info.has_emission == 1 and abs(vol.rec.vdb_info.max_density - 12.4696) < 1e-3
+    scene = V.Scene([vol.instance()], env=synthetic_env(512, 256))
+    kw = dict(ray_depth=2, volume_depth=6, emission_scale=1.0, emission_pivot=1.0)
+    mine = V.Renderer(scene, 320, 180, kp=make_kp(**kw)); ref = V.Renderer(scene, 320, 180, kp=make_kp(**kw), cam=mine.cam)
+    orc = oracle_ref.RefOracle()
+    ref.params.p_oct.value = orc.build_octree(scene.h_volumes, 1)
+    scene.reset_blue_noise(); orc.render(ref, 2)
+    scene.reset_blue_noise(); mine.render(2); torch.cuda.synchronize()
+    assert float(ref.buffers.accum.mean()) > 1e-3
+    assert flipped_fraction(mine.buffers.accum.cpu().numpy(), ref.buffers.accum.cpu().numpy()) <= MAX_FLIPPED
+    assert flipped_fraction(mine.buffers.depth.cpu().numpy()[:, None], ref.buffers.depth.cpu().numpy()[:, None]) <= MAX_FLIPPED
+
+
+@needs_ref
+@pytest.mark.skipif(_big_asset("colored_smoke.vdb") is None, reason="colored_smoke.vdb not staged (oracle/_ref/assets)")
+def test_colored_smoke_against_reference():
+    vol = V.Volume.load_vdb(_big_asset("colored_smoke.vdb"))
+    assert vol.rec.vdb_info.has_color == 1
+    scene = V.Scene([vol.instance()], env=synthetic_env(512, 256))
+    kw = dict(ray_depth=2, volume_depth=4, density_mult=4.0)
+    mine = V.Renderer(scene, 320, 180, kp=make_kp(**kw)); ref = V.Renderer(scene, 320, 180, kp=make_kp(**kw), cam=mine.cam)
+    orc = oracle_ref.RefOracle()
+    scene.reset_blue_noise(); orc.render(ref, 2)
+    scene.reset_blue_noise(); mine.render(2); torch.cuda.synchronize()
+    a = ref.buffers.accum.cpu().numpy()
+    assert np.abs(a[:, 0] - a[:, 2]).max() > 1e-3, "the colour grid should tint the radiance"
+    assert flipped_fraction(mine.buffers.accum.cpu().numpy(), a) <= MAX_FLIPPED
+
+
+@needs_ref
+def test_many_instances_against_reference(dragon):
+    """BASELINE config 5 shape (instanced dragon through the octree's leaf lists) at the size the oracle finishes quickly."""
+    rng = np.random.RandomState(11)
+    inst = []
+    for i in range(120):
+        q = rng.randn(4); q /= np.linalg.norm(q)
+        inst.append(dragon.instance(pos=tuple(rng.uniform(-25, 25, 3)), quat=tuple(q), scale=float(rng.uniform(0.7, 1.3))))
+    scene = make_scene(dragon, instances=inst)
+    kw = dict(ray_depth=2)
+    mine = V.Renderer(scene, 256, 144, kp=make_kp(**kw)); ref = V.Renderer(scene, 256, 144, kp=make_kp(**kw), cam=mine.cam)
+    orc = oracle_ref.RefOracle()
+    scene.reset_blue_noise(); orc.render(ref, 1)
+    scene.reset_blue_noise(); mine.render(1); torch.cuda.synchronize()
+    assert float(ref.buffers.accum.mean()) > 1e-4
+    assert flipped_fraction(mine.buffers.accum.cpu().numpy(), ref.buffers.accum.cpu().numpy()) <= MAX_FLIPPED
+
+
 # ---- size-independent properties at the BASELINE resolution (no oracle needed) ------------------------------------
 def test_fused_passes_equal_single_passes_bitwise_full_hd(dragon):
     scene = make_scene(dragon)
