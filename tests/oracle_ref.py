@@ -38,7 +38,19 @@ class RefOracle:
         L.vptref_update_camera.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float]
         L.vptref_bounds.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.vptref_instance_xform.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float)]
+        L.vptref_atmosphere_init.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
+        L.vptref_atmosphere_init.restype = C.c_int
         self._loaded = False
+
+    def atmosphere_init(self, atmos, use_constant_solar_spectrum=True, use_ozone=True, luminance=0, white_balance=True, exposure=1.0):
+        """Run the reference's own Bruneton precompute (atmosphere::init, defaults of main.cpp:1433-1436) and
+        write the resulting AtmosphereParameters (scalars + the four look-up textures) into `atmos` in place."""
+        if not os.path.exists(os.path.join(REF_DIR, "atmo", "atmosphere_kernels.ptx")):
+            raise RuntimeError("oracle/_ref/atmo is not built")
+        assert C.sizeof(atmos) == 464
+        rc = self.lib.vptref_atmosphere_init(os.path.join(REF_DIR, "atmo").encode(), int(use_constant_solar_spectrum), int(use_ozone),
+                                             int(luminance), int(white_balance), float(exposure), C.cast(C.byref(atmos), C.c_void_p))
+        if rc: raise RuntimeError(f"vptref_atmosphere_init -> {rc}")
 
     def load_kernels(self):
         if self._loaded:

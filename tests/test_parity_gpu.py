@@ -217,6 +217,31 @@ def test_many_instances_against_reference(dragon):
 
 
 # ---- size-independent properties at the BASELINE resolution (no oracle needed) ------------------------------------
+@needs_ref
+@pytest.mark.skipif(not os.path.exists(os.path.join(oracle_ref.REF_DIR, "atmo", "atmosphere_kernels.ptx")), reason="oracle/_ref/atmo not built")
+@pytest.mark.parametrize("cfg", [
+    dict(W=512, H=512, passes=1, elevation=30.0, kp=dict(ray_depth=1)),                          # BASELINE config 1 literally (env type 0)
+    dict(W=320, H=200, passes=3, elevation=4.0, kp=dict(ray_depth=20, sky_mult=2.0)),            # low sun, multi-pass, deeper paths
+    dict(W=256, H=128, passes=2, elevation=60.0, luminance=2, aperture=0.2, kp=dict(ray_depth=3)),  # luminance mode + thin lens (env_pos != cam origin)
+])
+def test_precomputed_sky_environment_against_reference(dragon, cfg):
+    """environment_type == 0: both kernels read the SAME look-up textures, produced by the reference's own precompute."""
+    scene = make_scene(dragon)
+    orc = oracle_ref.RefOracle()
+    orc.atmosphere_init(scene.atmos, luminance=cfg.get("luminance", 0))
+    kw = dict(environment_type=0, elevation=cfg["elevation"], **cfg["kp"])
+    cam = scene.frame_camera(cfg["W"], cfg["H"], aperture=cfg.get("aperture", 0.0))
+    mine = V.Renderer(scene, cfg["W"], cfg["H"], kp=make_kp(**kw), cam=cam)
+    ref = V.Renderer(scene, cfg["W"], cfg["H"], kp=make_kp(**kw), cam=cam)
+    scene.reset_blue_noise(); orc.render(ref, cfg["passes"])
+    scene.reset_blue_noise(); mine.render(cfg["passes"]); torch.cuda.synchronize()
+    want = ref.buffers.accum.cpu().numpy(); got = mine.buffers.accum.cpu().numpy()
+    assert np.isfinite(want).all() and float(want.mean()) > 1e-3, "the sky must actually light the frame"
+    assert want.reshape(cfg["H"], cfg["W"], 3)[0].std() > 0 or want.std() > 0
+    assert flipped_fraction(got, want) <= MAX_FLIPPED
+    assert flipped_fraction(mine.buffers.depth.cpu().numpy()[:, None], ref.buffers.depth.cpu().numpy()[:, None]) <= MAX_FLIPPED
+
+
 def test_fused_passes_equal_single_passes_bitwise_full_hd(dragon):
     scene = make_scene(dragon)
     a = V.Renderer(scene, 1920, 1080, kp=make_kp(ray_depth=100), options=dict(passes_per_chunk=4))
@@ -265,4 +290,8 @@ def test_unsupported_configurations_fail_loudly(dragon):
     scene = make_scene(dragon)
     r = V.Renderer(scene, 64, 64, kp=make_kp(integrator=1))
     with pytest.raises(V.VptError, match="integrator"):
+        r.render_pass()
+    scene.atmos.transmittance_texture = 0                                   # sky environment without its look-up textures
+    r = V.Renderer(scene, 64, 64, kp=make_kp(environment_type=0))
+    with pytest.raises(V.VptError, match="atmosphere"):
         r.render_pass()

@@ -14,7 +14,9 @@
 //
 // Numerics: compiled with the reference's flags (--use_fast_math); decision-relevant expressions keep
 // the reference's operand order so a pixel's path is reproduced sample for sample (see vpt_math.cuh).
+#include <type_traits>
 #include "vpt_walk.cuh"
+#include "vpt_atmosphere.cuh"
 #include "vpt_kernels.h"
 
 namespace vpt {
@@ -304,15 +306,21 @@ VPT_DEV float3 mat3_mul(const float m[9], float3 v) {
     return f3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
 }
 
+// kSky: environment_type == 0 (Bruneton sky lookup, `atmo` is the caller's AtmosphereParameters); the HDRI variant
+// takes a 16-byte dummy so it keeps its small parameter block and register budget.
+struct NoSky { int pad[4]; };
+
+template <bool kSky>
 __global__ void __launch_bounds__(256)
-k_resolve(const FrameArgs fa, const int n_passes, const int sampled, const int write_display)
+k_resolve(const FrameArgs fa, const typename std::conditional<kSky, vpt_atmosphere, NoSky>::type atmo,
+          const int n_passes, const int sampled, const int write_display)
 {
     const FrameGeom& g = fa.geom;
     const vpt_kernel_params& kp = fa.kp;
     const vpt_camera& cam = fa.cam;
     const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
     if (lp >= (uint32_t)g.n_local) return;
-    const int lr = lp / g.width, x = lp - lr * g.width;
+    const int lr = lp / g.width;
     const int y = global_row(g, lr);
     if (y >= g.height) return;
 
@@ -340,9 +348,10 @@ k_resolve(const FrameArgs fa, const int n_passes, const int sampled, const int w
                 beta = f3(C.x, C.y, C.z); L = f3(B.x, B.y, B.z);
                 depth = B.w; tr = A.w;
             }
-            if (kp.environment_type == 0) {
-                // Bruneton sky (reference sample_atmosphere): not part of this build yet; the host API
-                // refuses environment_type == 0, so this branch is never taken.
+            if constexpr (kSky) {
+                // precomputed sky seen from env_pos along the final direction (:1838-1841)
+                const float4 D = fa.planeD[s];
+                L += sample_atmosphere(atmo, kp.azimuth, kp.elevation, f3(D.x, D.y, D.z), ray_dir) * beta * kp.sky_mult * ld3(kp.sky_color);
             } else {
                 const float4 texval = tex2D<float4>((cudaTextureObject_t)kp.env_tex,
                     atan2f(ray_dir.z, ray_dir.x) * (float)(0.5 / 3.14159265358979323846) + 0.5f,
@@ -475,10 +484,12 @@ int trace_max_ctas_per_sm()
     return n;
 }
 
-cudaError_t launch_resolve(const FrameArgs& fa, int n_passes, int sampled, int write_display, cudaStream_t s)
+cudaError_t launch_resolve(const FrameArgs& fa, const vpt_atmosphere* sky, int n_passes, int sampled, int write_display, cudaStream_t s)
 {
     const int threads = 256;
-    k_resolve<<<(fa.geom.n_local + threads - 1) / threads, threads, 0, s>>>(fa, n_passes, sampled, write_display);
+    const int blocks = (fa.geom.n_local + threads - 1) / threads;
+    if (sky) k_resolve<true><<<blocks, threads, 0, s>>>(fa, *sky, n_passes, sampled, write_display);
+    else     k_resolve<false><<<blocks, threads, 0, s>>>(fa, NoSky{}, n_passes, sampled, write_display);
     return cudaGetLastError();
 }
 

@@ -52,7 +52,8 @@ cudaError_t launch_prepare_scene(const vpt_gpu_vdb* vols, const vpt_octnode* roo
 cudaError_t launch_generate(const FrameArgs& fa, int n_passes, cudaStream_t s);
 cudaError_t launch_trace(const FrameArgs& fa, int n_ctas, cudaStream_t s);
 int         trace_max_ctas_per_sm();
-cudaError_t launch_resolve(const FrameArgs& fa, int n_passes, int sampled, int write_display, cudaStream_t s);
+// sky != null selects the environment_type == 0 variant (host copy of the caller's AtmosphereParameters)
+cudaError_t launch_resolve(const FrameArgs& fa, const vpt_atmosphere* sky, int n_passes, int sampled, int write_display, cudaStream_t s);
 cudaError_t launch_bn_prepare(void* bn, float2* table, int np, cudaStream_t s);
 cudaError_t launch_bn_advance(void* bn, int n, cudaStream_t s);
 cudaError_t launch_unpermute(const void* gathered, void* full, const FrameGeom& g, int elem_bytes, cudaStream_t s);

@@ -220,8 +220,14 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
     const vpt_kernel_params& kp = fa.kp;
 
     if (kp.integrator != 0) return fail(c, VPT_ERR_UNSUPPORTED, "integrator != 0 (vol_integrator) is not implemented in this build");
-    if (kp.environment_type == 0 && kp.render && kp.iteration < kp.max_interactions)
-        return fail(c, VPT_ERR_UNSUPPORTED, "environment_type == 0 (Bruneton sky) is not implemented in this build; use an HDRI environment");
+    // environment_type == 0: the caller's AtmosphereParameters (scalars + the four precomputed look-up textures)
+    vpt_atmosphere atmo;
+    memcpy(&atmo, params[VPT_ARG_ATMOSPHERE], sizeof(vpt_atmosphere));
+    const bool sky_env = (kp.environment_type == 0);
+    if (sky_env && kp.render && kp.iteration < kp.max_interactions &&
+        (!atmo.transmittance_texture || !atmo.scattering_texture || !atmo.irradiance_texture || !atmo.single_mie_scattering_texture))
+        return fail(c, VPT_ERR_INVALID, "environment_type == 0 needs the four precomputed atmosphere textures in AtmosphereParameters");
+    const vpt_atmosphere* sky = sky_env ? &atmo : nullptr;
     if (!d_volumes || !d_sphere || !d_root) return fail(c, VPT_ERR_INVALID, "volumes / sphere / octree device pointer is null");
     if (!kp.accum_buffer || !kp.depth_buffer || !kp.cost_buffer || !kp.display_buffer || !kp.raw_buffer || !kp.blue_noise_buffer)
         return fail(c, VPT_ERR_INVALID, "Kernel_params output buffer pointer is null");
@@ -288,14 +294,14 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         VPT_CUDA(c, timed(0, [&] { return vpt::launch_generate(fa, (int)np, stream); }));
         VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, trace_ctas, stream); }));
         const bool last = (done + np == n_passes);
-        VPT_CUDA(c, timed(2, [&] { return vpt::launch_resolve(fa, (int)np, 1, last ? 1 : 0, stream); }));
+        VPT_CUDA(c, timed(2, [&] { return vpt::launch_resolve(fa, sky, (int)np, 1, last ? 1 : 0, stream); }));
         c->launches += 4;
         done += np;
     }
     if (n_sampled < n_passes) {
         // passes that no longer sample: WHITE / re-tonemap semantics of the kernel tail
         fa.kp.iteration = it0 + n_sampled;
-        VPT_CUDA(c, vpt::launch_resolve(fa, (int)(n_passes - n_sampled), 0, 1, stream));
+        VPT_CUDA(c, vpt::launch_resolve(fa, sky, (int)(n_passes - n_sampled), 0, 1, stream));
         VPT_CUDA(c, vpt::launch_bn_advance((void*)kp.blue_noise_buffer, (int)(n_passes - n_sampled), stream));
         c->launches += 2;
     }
