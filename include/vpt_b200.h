@@ -96,6 +96,14 @@ int  vpt_texture_create_3d(const float* host_data, int channels, int dim_x, int 
                            vpt_tex_t* tex_out, void** array_out);
 /* Equirectangular environment map float4 (main.cpp:945-978: wrap / clamp, linear, normalised). */
 int  vpt_texture_create_env(const float* host_rgba, unsigned width, unsigned height, vpt_tex_t* tex_out, void** array_out);
+/* The four sky-sampling tables the volumetric path integrator reads when environment_type == 0 (reference create_cdf,
+ * main.cpp:647-867): from a res x res table of the sky's luminous power over (azimuth = x, elevation = y) builds the
+ * row-conditional cdf, the marginal function and its cdf, and wraps all four as point-sampled unnormalised float
+ * textures (2-D, 2-D, 1-D, 1-D).  tex_out / arrays_out order: env_func_tex, env_cdf_tex, env_marginal_func_tex,
+ * env_marginal_cdf_tex; *marginal_int_out is Kernel_params.env_marginal_int; env_sample_tex_res = res.  The reference's
+ * version reads/writes one element outside its arrays at the row starts (cdf_p - 1, marginal_cdf_p - 1); this one
+ * uses 0 for those out-of-range reads. */
+int  vpt_env_tables_create(const float* func, unsigned res, vpt_tex_t tex_out[4], void* arrays_out[4], float* marginal_int_out);
 int  vpt_texture_destroy(vpt_tex_t tex, void* array);
 
 /* Minimal OpenVDB (file format 224) reader: densify grid `grid_name` over its active-voxel bounding box

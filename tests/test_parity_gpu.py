@@ -246,6 +246,51 @@ def test_precomputed_sky_environment_against_reference(dragon, cfg):
     assert flipped_fraction(mine.buffers.depth.cpu().numpy()[:, None], ref.buffers.depth.cpu().numpy()[:, None]) <= MAX_FLIPPED
 
 
+def _sky_power_table(res=180, sun_az=2.0, sun_el=1.0):
+    """A smooth, strictly positive stand-in for the sky's luminous power over (azimuth, elevation): what the reference's
+    create_cdf tabulates from its host-side sky model.  Both kernels sample from the same tables."""
+    el = (np.arange(res, dtype=np.float32) / (res - 1) * np.pi)[:, None]
+    az = (np.arange(res, dtype=np.float32) / (res - 1) * 2 * np.pi)[None, :]
+    return (0.05 + np.sin(el) * (1.2 + np.cos(az - sun_az)) * (0.3 + np.exp(-4.0 * (el - sun_el) ** 2))).astype(np.float32)
+
+
+@needs_ref
+@pytest.mark.skipif(not os.path.exists(os.path.join(oracle_ref.REF_DIR, "atmo", "atmosphere_kernels.ptx")), reason="oracle/_ref/atmo not built")
+@pytest.mark.parametrize("cfg", [
+    dict(W=256, H=160, passes=2, env=1, kp=dict(ray_depth=8)),                                    # HDRI sky estimator (uniform sphere + HG MIS)
+    dict(W=256, H=160, passes=2, env=1, kp=dict(ray_depth=100, phase_g1=0.6, density_mult=3.0)),  # cfg 2's "true multiple scattering" variant
+    dict(W=200, H=120, passes=2, env=0, kp=dict(ray_depth=6)),                                    # tabulated sky sampling (env-CDF MIS)
+    dict(W=200, H=120, passes=1, env=1, lights=True, kp=dict(ray_depth=5, sky_mult=0.0)),         # point lights, sky class switched off
+    dict(W=160, H=100, passes=1, env=1, sphere=True, aperture=0.15, kp=dict(ray_depth=4)),        # sphere in the way + thin lens
+])
+def test_volumetric_path_integrator_against_reference(dragon, cfg):
+    """Kernel_params.integrator = 1 (reference vol_integrator): light-class selection, NEE per scatter, sky MIS, sky tail."""
+    lights = [((9.0, 6.0, 2.0), (1.0, 0.8, 0.6), 40.0), ((-2.0, 3.0, 8.0), (0.5, 0.7, 1.0), 25.0)] if cfg.get("lights") else None
+    scene = make_scene(dragon, lights=lights)
+    if cfg.get("sphere"):
+        sp = scene.h_sphere; sp.center = V.f3(6.0, 6.0, 5.0); sp.radius = 1.0
+        scene.d_sphere.copy_(torch.frombuffer(bytearray(bytes(sp)), dtype=torch.uint8))
+    orc = oracle_ref.RefOracle()
+    orc.atmosphere_init(scene.atmos)
+    tables = V.EnvTables(_sky_power_table())
+    kw = dict(integrator=1, environment_type=cfg["env"], **cfg["kp"])
+    cam = scene.frame_camera(cfg["W"], cfg["H"], aperture=cfg.get("aperture", 0.0))
+    mine = V.Renderer(scene, cfg["W"], cfg["H"], kp=make_kp(**kw), cam=cam)
+    ref = V.Renderer(scene, cfg["W"], cfg["H"], kp=make_kp(**kw), cam=cam)
+    tables.apply(mine.kp); tables.apply(ref.kp)
+    scene.reset_blue_noise(); orc.render(ref, cfg["passes"])
+    scene.reset_blue_noise(); mine.render(cfg["passes"]); torch.cuda.synchronize()
+    want = ref.buffers.accum.cpu().numpy(); got = mine.buffers.accum.cpu().numpy()
+    frac = flipped_fraction(got, want)
+    dfrac = flipped_fraction(mine.buffers.depth.cpu().numpy()[:, None], ref.buffers.depth.cpu().numpy()[:, None])
+    print(f"vol cfg {cfg}: ref mean {float(want.mean()):.6g} ours {float(got.mean()):.6g} flipped {frac:.3g} depth-flipped {dfrac:.3g}")
+    assert np.isfinite(want).all() and float(want.mean()) > 1e-3
+    assert frac <= MAX_FLIPPED and dfrac <= MAX_FLIPPED
+    raw_m = mine.buffers.raw.cpu().numpy().reshape(-1, 4)[:, 3]; raw_r = ref.buffers.raw.cpu().numpy().reshape(-1, 4)[:, 3]
+    assert np.mean(np.abs(raw_m - raw_r) > 1e-5) <= MAX_FLIPPED
+    tables.destroy()
+
+
 def test_fused_passes_equal_single_passes_bitwise_full_hd(dragon):
     scene = make_scene(dragon)
     a = V.Renderer(scene, 1920, 1080, kp=make_kp(ray_depth=100), options=dict(passes_per_chunk=4))
@@ -292,8 +337,8 @@ def test_iteration_limit_and_render_flag_semantics(dragon):
 
 def test_unsupported_configurations_fail_loudly(dragon):
     scene = make_scene(dragon)
-    r = V.Renderer(scene, 64, 64, kp=make_kp(integrator=1))
-    with pytest.raises(V.VptError, match="integrator"):
+    r = V.Renderer(scene, 64, 64, kp=make_kp(integrator=1, environment_type=0))   # no sampling tables in Kernel_params
+    with pytest.raises(V.VptError, match="sampling tables"):
         r.render_pass()
     scene.atmos.transmittance_texture = 0                                   # sky environment without its look-up textures
     r = V.Renderer(scene, 64, 64, kp=make_kp(environment_type=0))

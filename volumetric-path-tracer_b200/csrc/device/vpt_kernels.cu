@@ -260,7 +260,10 @@ k_generate(const FrameArgs fa)
             int leaf = -2;
             if (!aabb_contains(sc.root_pmin, sc.root_pmax, p)) leaf = -1;
             for (int it = 0; it < 256 && leaf == -2; ++it) leaf = oct_locate_or_skip(fs.oct, sc, p, dir);
-            if (leaf == -1) hit = false;                         // walked out through empty space: sample == miss sample
+            if (leaf == -1) {                                    // walked out through empty space: sample == miss sample
+                hit = false;
+                if (kp.integrator != 0) dir = normalize(dir);    // vol_integrator renormalises after a box hit (:1747)
+            }
             else if (leaf >= 0) { prestepped = true; wstart = p; }
             // leaf == -2 after 256 hops: leave it to the generic route
         }
@@ -306,13 +309,14 @@ VPT_DEV float3 mat3_mul(const float m[9], float3 v) {
     return f3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
 }
 
-// kSky: environment_type == 0 (Bruneton sky lookup, `atmo` is the caller's AtmosphereParameters); the HDRI variant
+// kSky 1: direct integrator with environment_type == 0 (Bruneton sky lookup, `atmo` is the caller's AtmosphereParameters);
+// kSky 2: volumetric path integrator, which always ends on the sky (:1752); kSky 0: HDRI environment -- that variant
 // takes a 16-byte dummy so it keeps its small parameter block and register budget.
 struct NoSky { int pad[4]; };
 
-template <bool kSky>
+template <int kSky>
 __global__ void __launch_bounds__(256)
-k_resolve(const FrameArgs fa, const typename std::conditional<kSky, vpt_atmosphere, NoSky>::type atmo,
+k_resolve(const FrameArgs fa, const typename std::conditional<kSky != 0, vpt_atmosphere, NoSky>::type atmo,
           const int n_passes, const int sampled, const int write_display)
 {
     const FrameGeom& g = fa.geom;
@@ -348,10 +352,13 @@ k_resolve(const FrameArgs fa, const typename std::conditional<kSky, vpt_atmosphe
                 beta = f3(C.x, C.y, C.z); L = f3(B.x, B.y, B.z);
                 depth = B.w; tr = A.w;
             }
-            if constexpr (kSky) {
+            if constexpr (kSky == 1) {
                 // precomputed sky seen from env_pos along the final direction (:1838-1841)
                 const float4 D = fa.planeD[s];
                 L += sample_atmosphere(atmo, kp.azimuth, kp.elevation, f3(D.x, D.y, D.z), ray_dir) * beta * kp.sky_mult * ld3(kp.sky_color);
+            } else if constexpr (kSky == 2) {
+                const float4 D = fa.planeD[s];                       // env_pos or the last path position (:1750-1752)
+                L += beta * sample_atmosphere(atmo, kp.azimuth, kp.elevation, f3(D.x, D.y, D.z), ray_dir);
             } else {
                 const float4 texval = tex2D<float4>((cudaTextureObject_t)kp.env_tex,
                     atan2f(ray_dir.z, ray_dir.x) * (float)(0.5 / 3.14159265358979323846) + 0.5f,
@@ -464,23 +471,31 @@ cudaError_t launch_generate(const FrameArgs& fa, int n_passes, cudaStream_t s)
 
 static size_t trace_smem_bytes() { return (size_t)kTraceWarps * kRayWords * kPool * sizeof(float); }
 
-cudaError_t launch_trace(const FrameArgs& fa, int n_ctas, cudaStream_t s)
+// atm != null selects the volumetric path integrator variant (Kernel_params.integrator != 0)
+cudaError_t launch_trace(const FrameArgs& fa, const vpt_atmosphere* atm, int n_ctas, cudaStream_t s)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
+        cudaError_t e = cudaFuncSetAttribute(k_trace<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k_trace<<<n_ctas, kTraceThreads, trace_smem_bytes(), s>>>(fa);
+    if (atm) k_trace<1><<<n_ctas, kTraceThreads, trace_smem_bytes(), s>>>(fa, *atm);
+    else     k_trace<0><<<n_ctas, kTraceThreads, trace_smem_bytes(), s>>>(fa, NoAtmo{});
     return cudaGetLastError();
 }
 
-int trace_max_ctas_per_sm()
+int trace_max_ctas_per_sm(int integrator)
 {
     int n = 0;
-    cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace, kTraceThreads, trace_smem_bytes());
+    if (integrator) {
+        cudaFuncSetAttribute(k_trace<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<1>, kTraceThreads, trace_smem_bytes());
+    } else {
+        cudaFuncSetAttribute(k_trace<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<0>, kTraceThreads, trace_smem_bytes());
+    }
     return n;
 }
 
@@ -488,8 +503,9 @@ cudaError_t launch_resolve(const FrameArgs& fa, const vpt_atmosphere* sky, int n
 {
     const int threads = 256;
     const int blocks = (fa.geom.n_local + threads - 1) / threads;
-    if (sky) k_resolve<true><<<blocks, threads, 0, s>>>(fa, *sky, n_passes, sampled, write_display);
-    else     k_resolve<false><<<blocks, threads, 0, s>>>(fa, NoSky{}, n_passes, sampled, write_display);
+    if (sky && fa.kp.integrator != 0) k_resolve<2><<<blocks, threads, 0, s>>>(fa, *sky, n_passes, sampled, write_display);
+    else if (sky)                     k_resolve<1><<<blocks, threads, 0, s>>>(fa, *sky, n_passes, sampled, write_display);
+    else                              k_resolve<0><<<blocks, threads, 0, s>>>(fa, NoSky{}, n_passes, sampled, write_display);
     return cudaGetLastError();
 }
 

@@ -386,17 +386,29 @@ VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, 
     }
 }
 
+#include "vpt_trace_vol.cuh"
+
+template <int kInteg>
 VPT_DEV void write_sample(const PathState& st, const FrameArgs& fa)
 {
     const size_t o = (size_t)st.pass * fa.geom.n_local + st.lp;
     fa.planeA[o] = make_float4(st.dir.x, st.dir.y, st.dir.z, st.alpha);                 // final direction, tr
     fa.planeB[o] = make_float4(st.L.x, st.L.y, st.L.z, st.depth);                       // L, depth
     fa.planeC[o] = make_float4(st.beta.x, st.beta.y, st.beta.z, 1.f);                   // beta
-    if (fa.planeD && !st.sphere_bounced) fa.planeD[o] = make_float4(st.org.x, st.org.y, st.org.z, 0.f);   // env_pos = camera origin unless the sphere branch moved it
+    if (kInteg) {
+        // vol_integrator evaluates the sky from env_pos while the throughput is still ~white, else from where the path ended (:1750)
+        const float3 e = length(st.beta) > 0.9999f ? st.org : st.pos;
+        fa.planeD[o] = make_float4(e.x, e.y, e.z, 0.f);
+    } else if (fa.planeD && !st.sphere_bounced) fa.planeD[o] = make_float4(st.org.x, st.org.y, st.org.z, 0.f);   // env_pos = camera origin unless the sphere branch moved it
 }
 
+// kInteg = 0: direct integrator (the tuned headline path); kInteg = 1: volumetric path integrator, which additionally needs the
+// caller's AtmosphereParameters in the kernel (sky radiance decides whether a transmittance walk is run at all)
+struct NoAtmo { int pad[4]; };
+
+template <int kInteg>
 __global__ void __launch_bounds__(kTraceThreads, kTraceMinCtas)
-k_trace(const FrameArgs fa)
+k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atmosphere, NoAtmo>::type atm)
 {
     __shared__ FrameShared fs;
     extern __shared__ float pool_smem[];                         // kTraceWarps x kRayWords x kPool words (opt-in dynamic shared memory)
@@ -449,13 +461,13 @@ k_trace(const FrameArgs fa)
                 st.mi = false; st.first_walk = true; st.sphere_bounced = false; st.rd = 1; st.vd = 1; st.light_budget = 0; st.light_index = 0;
                 st.mode = W_DELTA; st.exit_reason = EX_NONE; st.tr_kind = TR_SUN;
                 st.tmin_c = r0.w; st.obj_c = (int)((id.y >> 16) & 3u); st.have_closest = true;       // k_generate already ran the first test
-                st.phase = PH_BOUNCE_TOP; st.sphere_free = false; st.op = OP_GLUE;
+                st.phase = kInteg ? (int)VP_START : (int)PH_BOUNCE_TOP; st.sphere_free = false; st.op = OP_GLUE;
                 if ((id.y >> 18) & 1u) {
                     // k_generate already hopped over the empty nodes in front of this ray: it is a delta walker at `wpos`
                     const float4 ws = __ldg(fa.queue_aux + slot);
                     st.wpos = f3(ws.x, ws.y, ws.z); st.pos = st.wpos;
                     st.have_closest = false; st.sphere_free = true;
-                    st.phase = PH_AFTER_DELTA; st.op = OP_STEP;
+                    st.phase = kInteg ? (int)VP_AFTER_DELTA : (int)PH_AFTER_DELTA; st.op = OP_STEP;
                 }
                 store_ray(pv, j, st);
                 if (j == 0) tag0 = st.op; else if (j == 1) tag1 = st.op; else tag2 = st.op;
@@ -484,9 +496,12 @@ k_trace(const FrameArgs fa)
                     st.obj_c = closest_object(sc, sph, st.pos, st.dir, st.tmin_c);
                     st.have_closest = true; st.op = OP_GLUE;
                 }
-                if (st.op == OP_GLUE) advance(st, fs, fa, tc, sph);
+                if (st.op == OP_GLUE) {
+                    if constexpr (kInteg != 0) advance_vol(st, fs, fa, atm, tc, sph);
+                    else advance(st, fs, fa, tc, sph);
+                }
                 if (st.op == OP_TRBEGIN) begin_ratio_walk(st, fs, tc, sph);
-                if (st.op == OP_FINISH) { write_sample(st, fa); st.op = OP_IDLE; }
+                if (st.op == OP_FINISH) { write_sample<kInteg>(st, fa); st.op = OP_IDLE; }
                 else store_ray(pv, j, st);
                 if (j == 0) tag0 = st.op; else if (j == 1) tag1 = st.op; else tag2 = st.op;
                 lane_ops++;

@@ -226,7 +226,8 @@ VPT_DEV float hg_phase(float cos_theta, float g) {           // reference henyey
     return VPT_PI_4_F * (1 - g * g) / (denominator * sqrtf(denominator));
 }
 
-VPT_DEV void hg_sample(float3& wo, Rng& rng, float g) {       // reference sample_hg, render_kernel.cu:306-325
+// returns cos_theta of the sampled deflection (the reference returns henyey_greenstein(-cos_theta, g), used by integrator 1)
+VPT_DEV float hg_sample(float3& wo, Rng& rng, float g) {      // reference sample_hg, render_kernel.cu:306-325
     float cos_theta;
     if (fabsf(g) < VPT_EPS) { const float u = rng.next(); cos_theta = psub(1.0f, padd(u, u)); }
     else {
@@ -250,6 +251,7 @@ VPT_DEV void hg_sample(float3& wo, Rng& rng, float g) {       // reference sampl
     wo = make_float3(pfma(wo.x, cos_theta, pfma(xs.x, cp, pmul(sp, ys.x))),
                      pfma(wo.y, cos_theta, pfma(xs.y, cp, pmul(sp, ys.y))),
                      pfma(wo.z, cos_theta, pfma(xs.z, cp, pmul(sp, ys.z))));
+    return cos_theta;
 }
 
 VPT_DEV float3 sun_direction(float azimuth, float elevation) {  // reference degree_to_cartesian, :126-142

@@ -21,6 +21,7 @@
 #include <fstream>
 #include <iterator>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 namespace vpt {
@@ -219,14 +220,20 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
     memcpy(&d_root, params[VPT_ARG_OCTREE], 8);
     const vpt_kernel_params& kp = fa.kp;
 
-    if (kp.integrator != 0) return fail(c, VPT_ERR_UNSUPPORTED, "integrator != 0 (vol_integrator) is not implemented in this build");
     // environment_type == 0: the caller's AtmosphereParameters (scalars + the four precomputed look-up textures)
     vpt_atmosphere atmo;
     memcpy(&atmo, params[VPT_ARG_ATMOSPHERE], sizeof(vpt_atmosphere));
-    const bool sky_env = (kp.environment_type == 0);
-    if (sky_env && kp.render && kp.iteration < kp.max_interactions &&
+    const bool vol_integ = (kp.integrator != 0);             // vol_integrator always ends on the precomputed sky (:1752)
+    const bool sky_env = (kp.environment_type == 0) || vol_integ;
+    const bool samples = kp.render && kp.iteration < kp.max_interactions;
+    if (sky_env && samples &&
         (!atmo.transmittance_texture || !atmo.scattering_texture || !atmo.irradiance_texture || !atmo.single_mie_scattering_texture))
-        return fail(c, VPT_ERR_INVALID, "environment_type == 0 needs the four precomputed atmosphere textures in AtmosphereParameters");
+        return fail(c, VPT_ERR_INVALID, "environment_type == 0 / integrator != 0 need the four precomputed atmosphere textures in AtmosphereParameters");
+    if (vol_integ && samples && kp.environment_type == 0 && kp.sky_mult > 0.0f &&
+        (!kp.env_func_tex || !kp.env_cdf_tex || !kp.env_marginal_func_tex || !kp.env_marginal_cdf_tex || kp.env_sample_tex_res < 2))
+        return fail(c, VPT_ERR_INVALID, "integrator != 0 with environment_type == 0 needs the env sampling tables (env_*_tex, env_sample_tex_res) in Kernel_params");
+    if (vol_integ && samples && kp.environment_type != 0 && !kp.env_tex)
+        return fail(c, VPT_ERR_INVALID, "environment_type != 0 needs Kernel_params.env_tex");
     const vpt_atmosphere* sky = sky_env ? &atmo : nullptr;
     if (!d_volumes || !d_sphere || !d_root) return fail(c, VPT_ERR_INVALID, "volumes / sphere / octree device pointer is null");
     if (!kp.accum_buffer || !kp.depth_buffer || !kp.cost_buffer || !kp.display_buffer || !kp.raw_buffer || !kp.blue_noise_buffer)
@@ -253,7 +260,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
     }
 
     const int chunk = c->passes_per_chunk;
-    const bool planeD = (kp.environment_type == 0);
+    const bool planeD = sky_env;
     if (n_sampled) {
         const size_t per_chunk = (size_t)fa.geom.n_local * (size_t)(n_sampled < (unsigned)chunk ? n_sampled : (unsigned)chunk);
         int rc = ensure_frame_buffers(c, per_chunk, planeD);
@@ -269,7 +276,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
     fa.queue_count = c->d_counters; fa.queue_head = c->d_counters + 1;
     fa.planeA = c->d_planeA; fa.planeB = c->d_planeB; fa.planeC = c->d_planeC; fa.planeD = planeD ? c->d_planeD : nullptr;
 
-    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : vpt::trace_max_ctas_per_sm();
+    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : vpt::trace_max_ctas_per_sm(vol_integ ? 1 : 0);
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int trace_ctas = c->num_sms * ctas_per_sm;
 
@@ -292,7 +299,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         VPT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned) * 2, stream));
         VPT_CUDA(c, timed(3, [&] { return vpt::launch_bn_prepare((void*)kp.blue_noise_buffer, c->d_bn_table, (int)np, stream); }));   // jitter table + advance
         VPT_CUDA(c, timed(0, [&] { return vpt::launch_generate(fa, (int)np, stream); }));
-        VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, trace_ctas, stream); }));
+        VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, vol_integ ? &atmo : nullptr, trace_ctas, stream); }));
         const bool last = (done + np == n_passes);
         VPT_CUDA(c, timed(2, [&] { return vpt::launch_resolve(fa, sky, (int)np, 1, last ? 1 : 0, stream); }));
         c->launches += 4;
@@ -378,6 +385,55 @@ int vpt_texture_create_env(const float* rgba, unsigned w, unsigned h, vpt_tex_t*
     cudaTextureObject_t tex = 0;
     VPT_CUDA(nullptr, cudaCreateTextureObject(&tex, &res, &td, NULL));
     *tex_out = (vpt_tex_t)tex; *array_out = (void*)arr;
+    return VPT_OK;
+}
+
+// point-sampled, unnormalised float table (h == 0: 1-D array), the descriptor main.cpp:788-867 uses for the env sampling tables
+static int create_table_texture(const float* data, unsigned w, unsigned h, vpt_tex_t* tex_out, void** array_out) {
+    const cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+    cudaArray_t arr = nullptr;
+    VPT_CUDA(nullptr, cudaMallocArray(&arr, &desc, w, h));
+    VPT_CUDA(nullptr, cudaMemcpy2DToArray(arr, 0, 0, data, (size_t)w * sizeof(float), (size_t)w * sizeof(float), h ? h : 1, cudaMemcpyHostToDevice));
+    cudaResourceDesc res; memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray; res.res.array.array = arr;
+    cudaTextureDesc td; memset(&td, 0, sizeof(td));
+    td.addressMode[0] = cudaAddressModeWrap; td.addressMode[1] = h ? cudaAddressModeClamp : cudaAddressModeWrap; td.addressMode[2] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+    cudaTextureObject_t tex = 0;
+    VPT_CUDA(nullptr, cudaCreateTextureObject(&tex, &res, &td, NULL));
+    *tex_out = (vpt_tex_t)tex; *array_out = (void*)arr;
+    return VPT_OK;
+}
+
+int vpt_env_tables_create(const float* func, unsigned res, vpt_tex_t tex_out[4], void* arrays_out[4], float* marginal_int_out) {
+    if (!func || res < 2 || !tex_out || !arrays_out || !marginal_int_out) return fail(nullptr, VPT_ERR_INVALID, "vpt_env_tables_create: bad arguments");
+    const size_t n = (size_t)res * res;
+    std::vector<float> cdf(n), mfunc(res), mcdf(res);
+    float total = 0.f;
+    for (unsigned y = 0; y < res; ++y) {
+        float run = 0.f;
+        for (unsigned x = 0; x < res; ++x) {                       // cdf[x] = sum of func[0..x-1] / res
+            if (x) run += func[(size_t)y * res + x - 1] / (float)res;
+            cdf[(size_t)y * res + x] = run;
+        }
+        mfunc[y] = run; total += run;
+    }
+    for (unsigned y = 0; y < res; ++y)
+        for (unsigned x = 0; x < res; ++x) {
+            float& c = cdf[(size_t)y * res + x];
+            if (total == 0.f) c = ((float)x / (float)res) * ((float)y / (float)res);
+            else { c /= mfunc[y]; if (x == res - 1) c = 1.0f; }
+        }
+    float run = 0.f;
+    for (unsigned y = 0; y < res; ++y) { run += mfunc[y] / (float)res; mcdf[y] = run; }
+    const float marginal_int = run;
+    if (marginal_int > 0.f) for (unsigned y = 0; y < res; ++y) mcdf[y] /= std::max(.000001f, marginal_int);
+    *marginal_int_out = marginal_int;
+    int rc;
+    if ((rc = create_table_texture(func, res, res, &tex_out[0], &arrays_out[0])) != VPT_OK) return rc;
+    if ((rc = create_table_texture(cdf.data(), res, res, &tex_out[1], &arrays_out[1])) != VPT_OK) return rc;
+    if ((rc = create_table_texture(mfunc.data(), res, 0, &tex_out[2], &arrays_out[2])) != VPT_OK) return rc;
+    if ((rc = create_table_texture(mcdf.data(), res, 0, &tex_out[3], &arrays_out[3])) != VPT_OK) return rc;
     return VPT_OK;
 }
 

@@ -66,6 +66,25 @@ def texture_env(rgba: np.ndarray) -> Texture:
     return Texture(tex.value, arr)
 
 
+class EnvTables:
+    """Sky-sampling tables of the volumetric path integrator (Kernel_params.env_*_tex), built by vpt_env_tables_create."""
+    def __init__(self, func: np.ndarray):
+        func = np.ascontiguousarray(func, dtype=np.float32)
+        assert func.ndim == 2 and func.shape[0] == func.shape[1]
+        self.res = int(func.shape[0])
+        tex = (C.c_uint64 * 4)(); arr = (C.c_void_p * 4)(); mint = C.c_float(0)
+        check(lib.vpt_env_tables_create(func.ctypes.data_as(C.POINTER(C.c_float)), self.res, tex, arr, C.byref(mint)), None, "vpt_env_tables_create")
+        self.textures = [Texture(tex[i], arr[i]) for i in range(4)]
+        self.marginal_int = float(mint.value)
+
+    def apply(self, kp):
+        kp.env_func_tex, kp.env_cdf_tex, kp.env_marginal_func_tex, kp.env_marginal_cdf_tex = (t.tex for t in self.textures)
+        kp.env_marginal_int = self.marginal_int; kp.env_sample_tex_res = self.res
+
+    def destroy(self):
+        for t in self.textures: t.destroy()
+
+
 def load_vdb_grid(path, grid):
     """-> (values (z,y,x[,3]) float32, info dict) or None when the grid is absent."""
     vals = C.POINTER(C.c_float)()
