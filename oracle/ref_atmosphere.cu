@@ -18,6 +18,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <new>
+#include <cstdlib>
 #include <unistd.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -41,7 +43,12 @@ extern "C" int vptref_atmosphere_init(const char* module_dir, int use_constant_s
     char cwd[4096];
     if (!getcwd(cwd, sizeof cwd)) return -1;
     if (chdir(module_dir) != 0) { fprintf(stderr, "[vptref] atmosphere: cannot enter %s\n", module_dir); return -2; }
-    g_atmo = new atmosphere();                       // a fresh model per call (init() appends to its spectra); the old one is kept alive for its textures
+    // A fresh model per call (init() appends to its spectra); the old one is kept alive for its textures.  The reference's
+    // object has static storage (main.cpp: `atmosphere earth_atmosphere;`) and relies on that zero-initialisation:
+    // copy_*_texture() destroys "the previous texture" whenever the handle member is non-zero (atmosphere.cpp:506).
+    // Give the object the same zeroed storage here, otherwise a stale heap word is destroyed as a texture handle.
+    void* storage = calloc(1, sizeof(atmosphere));
+    g_atmo = new (storage) atmosphere();
     g_atmo->m_use_constant_solar_spectrum = use_constant_solar_spectrum != 0;
     g_atmo->m_use_ozone = use_ozone != 0;
     g_atmo->m_use_luminance = luminance_mode == 1 ? APPROXIMATE : luminance_mode == 2 ? PRECOMPUTED : NONE;

@@ -13,6 +13,9 @@ REF_DIR = os.path.join(_REPO, "oracle", "_ref")
 LIB = os.path.join(REF_DIR, "libvpt_ref.so")
 
 
+_ATMO_CACHE = {}
+
+
 def available():
     return all(os.path.exists(os.path.join(REF_DIR, f)) for f in
                ("libvpt_ref.so", "render_kernel_ref.cubin", "render_kernel_ref_nobn.cubin", "bn_advance_ref.cubin"))
@@ -48,9 +51,14 @@ class RefOracle:
         if not os.path.exists(os.path.join(REF_DIR, "atmo", "atmosphere_kernels.ptx")):
             raise RuntimeError("oracle/_ref/atmo is not built")
         assert C.sizeof(atmos) == 464
-        rc = self.lib.vptref_atmosphere_init(os.path.join(REF_DIR, "atmo").encode(), int(use_constant_solar_spectrum), int(use_ozone),
-                                             int(luminance), int(white_balance), float(exposure), C.cast(C.byref(atmos), C.c_void_p))
-        if rc: raise RuntimeError(f"vptref_atmosphere_init -> {rc}")
+        key = (bool(use_constant_solar_spectrum), bool(use_ozone), int(luminance), bool(white_balance), float(exposure))
+        if key not in _ATMO_CACHE:                       # one precompute per model per process (the textures stay alive)
+            buf = (C.c_ubyte * 464)()
+            rc = self.lib.vptref_atmosphere_init(os.path.join(REF_DIR, "atmo").encode(), int(key[0]), int(key[1]),
+                                                 key[2], int(key[3]), key[4], C.cast(buf, C.c_void_p))
+            if rc: raise RuntimeError(f"vptref_atmosphere_init -> {rc}")
+            _ATMO_CACHE[key] = bytes(buf)
+        C.memmove(C.byref(atmos), _ATMO_CACHE[key], 464)
 
     def load_kernels(self):
         if self._loaded:
