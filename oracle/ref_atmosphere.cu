@@ -49,6 +49,28 @@ extern "C" int vptref_atmosphere_init(const char* module_dir, int use_constant_s
     // Give the object the same zeroed storage here, otherwise a stale heap word is destroyed as a texture handle.
     void* storage = calloc(1, sizeof(atmosphere));
     g_atmo = new (storage) atmosphere();
+    {
+        // The reference's precompute kernels index their scattering buffers with unclamped texel coordinates
+        // (atmosphere_kernels.cu:378-392: u = 1 maps to texel `size`, one row / slice past the end, up to ~0.5 MB beyond
+        // the allocation), which faults or not depending on what the driver mapped next to the buffer.  The buffer
+        // pointers are public members, so the harness re-homes the nine buffers into one zeroed slab with 2 MB of
+        // slack on both sides of each: the stray reads then land in mapped zeros, as they do in a lucky run.
+        AtmosphereParameters& P = g_atmo->atmosphere_parameters;
+        const size_t small = (size_t)TRANSMITTANCE_TEXTURE_WIDTH * TRANSMITTANCE_TEXTURE_HEIGHT * sizeof(float4);
+        const size_t irr = (size_t)IRRADIANCE_TEXTURE_WIDTH * IRRADIANCE_TEXTURE_HEIGHT * sizeof(float4);
+        const size_t big = (size_t)SCATTERING_TEXTURE_WIDTH * SCATTERING_TEXTURE_HEIGHT * SCATTERING_TEXTURE_DEPTH * sizeof(float4);
+        float4** slot[9] = { &P.transmittance_buffer, &P.delta_irradience_buffer, &P.irradiance_buffer, &P.delta_rayleigh_scattering_buffer,
+                             &P.delta_mie_scattering_buffer, &P.scattering_buffer, &P.optional_mie_single_scattering_buffer,
+                             &P.delta_scattering_density_buffer, &P.delta_multiple_scattering_buffer };
+        const size_t bytes[9] = { small, irr, irr, big, big, big, big, big, big };
+        const size_t slack = (size_t)2 << 20;
+        size_t total = slack;
+        for (int i = 0; i < 9; ++i) total += bytes[i] + slack;
+        char* slab = nullptr;
+        if (cudaMalloc(&slab, total) != cudaSuccess || cudaMemset(slab, 0, total) != cudaSuccess) { chdir(cwd); return -5; }
+        size_t off = slack;
+        for (int i = 0; i < 9; ++i) { cudaFree(*slot[i]); *slot[i] = reinterpret_cast<float4*>(slab + off); off += bytes[i] + slack; }
+    }
     g_atmo->m_use_constant_solar_spectrum = use_constant_solar_spectrum != 0;
     g_atmo->m_use_ozone = use_ozone != 0;
     g_atmo->m_use_luminance = luminance_mode == 1 ? APPROXIMATE : luminance_mode == 2 ? PRECOMPUTED : NONE;
