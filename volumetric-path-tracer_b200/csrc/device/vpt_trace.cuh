@@ -199,7 +199,7 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
             st.op = OP_GLUE; st.exit_reason = EX_SCATTER;
         }
     } else {
-        st.trv = pmul(st.trv, psub(1.0f, pmul(tc.sigma_r_inv, psub(density, tc.sigma_c))));
+        st.trv = pmul(st.trv, pfma(-tc.sigma_r_inv, psub(density, tc.sigma_c), 1.0f));   // 1 - (rho - sigma_c) * sigma_r_inv, fused as in the reference SASS
         if (length(f3(st.trv)) < VPT_EPS) { st.op = OP_GLUE; st.exit_reason = EX_TR_DONE; }
     }
 }
@@ -397,7 +397,9 @@ VPT_DEV void write_sample(const PathState& st, const FrameArgs& fa)
     fa.planeC[o] = make_float4(st.beta.x, st.beta.y, st.beta.z, 1.f);                   // beta
     if (kInteg) {
         // vol_integrator evaluates the sky from env_pos while the throughput is still ~white, else from where the path ended (:1750)
-        const float3 e = length(st.beta) > 0.9999f ? st.org : st.pos;
+        float3 e = length(st.beta) > 0.9999f ? st.org : st.pos;
+        if (fa.debug_flags & 16) e = st.org;                                                // development probes
+        if (fa.debug_flags & 32) e = st.pos;
         fa.planeD[o] = make_float4(e.x, e.y, e.z, 0.f);
     } else if (fa.planeD && !st.sphere_bounced) fa.planeD[o] = make_float4(st.org.x, st.org.y, st.org.z, 0.f);   // env_pos = camera origin unless the sphere branch moved it
 }

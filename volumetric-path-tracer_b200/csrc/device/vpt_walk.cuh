@@ -226,16 +226,19 @@ VPT_DEV float hg_phase(float cos_theta, float g) {           // reference henyey
     return VPT_PI_4_F * (1 - g * g) / (denominator * sqrtf(denominator));
 }
 
-// returns cos_theta of the sampled deflection (the reference returns henyey_greenstein(-cos_theta, g), used by integrator 1)
+// returns cos_theta of the sampled deflection (the reference returns henyey_greenstein(-cos_theta, g), used by integrator 1).
+// Operation order and fusion follow the reference build's SASS, not just its PTX: ptxas contracts the single-use products
+// that the PTX still shows as mul + sub (1 - g*g -> fma(-g, g, 1); a*b - c*d -> fma(a, b, -(c*d)); 1 - c*c -> fma(-c, c, 1)),
+// which matters when the cross products cancel (directions close to the y axis).
 VPT_DEV float hg_sample(float3& wo, Rng& rng, float g) {      // reference sample_hg, render_kernel.cu:306-325
     float cos_theta;
     if (fabsf(g) < VPT_EPS) { const float u = rng.next(); cos_theta = psub(1.0f, padd(u, u)); }
     else {
         const float g2 = padd(g, g);
-        const float sqr_term = psub(1.0f, pmul(g, g)) / pfma(g2, rng.next(), psub(1.0f, g));
-        cos_theta = psub(pfma(g, g, 1.0f), pmul(sqr_term, sqr_term)) / g2;
+        const float sqr_term = pfma(-g, g, 1.0f) / pfma(g2, rng.next(), psub(1.0f, g));
+        cos_theta = pfma(-sqr_term, sqr_term, pfma(g, g, 1.0f)) / g2;
     }
-    const float sin_theta = sqrtf(fmaxf(psub(1.0f, pmul(cos_theta, cos_theta)), .0f));
+    const float sin_theta = sqrtf(fmaxf(pfma(-cos_theta, cos_theta, 1.0f), .0f));
     const float phi = pmul(rng.next(), (float)(2.0 * 3.14159265358979323846));
     // orthonormal frame around -wo (reference coordinate_system, :92-102)
     const float3 v1 = make_float3(-wo.x, -wo.y, -wo.z);
@@ -243,7 +246,9 @@ VPT_DEV float hg_sample(float3& wo, Rng& rng, float g) {      // reference sampl
     if (fabsf(v1.x) > fabsf(v1.y)) v2 = f3(-v1.z, 0.0f, v1.x);
     else                           v2 = f3(0.0f, v1.z, -v1.y);
     v2 = normalize(v2);
-    const float3 v3 = normalize(cross(v1, v2));
+    // cross(v1, v2) with v1 = -wo, written on wo as the compiled reference evaluates it
+    float3 v3 = make_float3(pfma(wo.z, v2.y, -pmul(wo.y, v2.z)), pfma(wo.x, v2.z, -pmul(wo.z, v2.x)), pfma(wo.y, v2.x, -pmul(wo.x, v2.y)));
+    v3 = normalize(v3);
     // x*sin*cos(phi) + y*sin*sin(phi) + z*cos  ->  mul(y term), fma(x term), fma(z term)
     const float cp = cosf(phi), sp = sinf(phi);
     const float3 xs = make_float3(pmul(sin_theta, v2.x), pmul(sin_theta, v2.y), pmul(sin_theta, v2.z));
