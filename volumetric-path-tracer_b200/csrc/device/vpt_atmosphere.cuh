@@ -221,7 +221,7 @@ struct Sky {
 
     VPT_DEV float3 solar_radiance() const {
         const vpt_f3& si = a.solar_irradiance;
-        const float3 s = f3(si.x, si.y, si.z) / (float)(3.14159265358979323846 * a.sun_angular_radius * a.sun_angular_radius);
+        const float3 s = f3(si.x, si.y, si.z) / (VPT_PI_F * a.sun_angular_radius * a.sun_angular_radius);   // M_PI is a float in the reference (helper_math.h:47)
         return apply_luminance(s, a.sun_spectral_radiance_to_luminance);
     }
 };
@@ -248,7 +248,7 @@ VPT_DEV float3 sample_atmosphere(const vpt_atmosphere& atm, float azimuth, float
         float3 sky_irr;
         const float3 sun_irr = sky.sun_and_sky_irradiance(pt - centre, n, sun, sky_irr);
         const vpt_f3& ga = atm.ground_albedo;
-        ground = f3(ga.x, ga.y, ga.z) * (float)(1.0 / 3.14159265358979323846) * (sun_irr + sky_irr);
+        ground = f3(ga.x, ga.y, ga.z) * (float)(1.0 / VPT_PI_F) * (sun_irr + sky_irr);
         float3 t;
         const float3 in_scatter = sky.radiance_to_point(ray_pos - centre, pt - centre, sun, t);
         ground = ground * t + in_scatter;

@@ -36,7 +36,9 @@ VPT_DEV void operator*=(float3& a, float s) { a.x *= s; a.y *= s; a.z *= s; }
 // source line compiled to mul+sub in one version of the trace kernel and to fma in another, which moved a handful
 // of samples by one texture-filter quantum).  Everything that feeds a tracking decision is therefore spelled with
 // explicit single-rounding intrinsics, in the operation order of the reference build's PTX:
-//   x*x + y*y + z*z  ->  fma(z, z, fma(x, x, y*y))      a*b - c*d  ->  mul, mul, sub (never fused)
+//   x*x + y*y + z*z  ->  fma(z, z, fma(x, x, y*y))      a*b - c*d  ->  fma(a, b, -(c*d))
+// The PTX alone is not enough: ptxas contracts single-use `mul.ftz` results into the following `add/sub.ftz` (the PTX of
+// a cross product reads mul, mul, sub; its SASS is FMUL, FFMA).  The orders here are read off the SASS (nvdisasm -gi).
 VPT_DEV float  pmul(float a, float b) { return __fmul_rn(a, b); }
 VPT_DEV float  padd(float a, float b) { return __fadd_rn(a, b); }
 VPT_DEV float  psub(float a, float b) { return __fsub_rn(a, b); }
@@ -44,8 +46,9 @@ VPT_DEV float  pfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 VPT_DEV float  dot(float3 a, float3 b) { return pfma(a.z, b.z, pfma(a.x, b.x, pmul(a.y, b.y))); }
 VPT_DEV float  length(float3 v) { return sqrtf(dot(v, v)); }
 VPT_DEV float3 normalize(float3 v) { float inv = rsqrtf(dot(v, v)); return make_float3(pmul(v.x, inv), pmul(v.y, inv), pmul(v.z, inv)); }
+// a*b - c*d: the reference's PTX shows mul, mul, sub, but ptxas contracts the first product (SASS: FMUL c*d; FFMA a*b - t)
 VPT_DEV float3 cross(float3 a, float3 b) {
-    return make_float3(psub(pmul(a.y, b.z), pmul(a.z, b.y)), psub(pmul(a.z, b.x), pmul(a.x, b.z)), psub(pmul(a.x, b.y), pmul(a.y, b.x)));
+    return make_float3(pfma(a.y, b.z, -pmul(a.z, b.y)), pfma(a.z, b.x, -pmul(a.x, b.z)), pfma(a.x, b.y, -pmul(a.y, b.x)));
 }
 // p + d * t with one rounding per component (fma), the form every position update of the reference compiles to
 VPT_DEV float3 madd3(float3 p, float3 d, float t) { return make_float3(pfma(d.x, t, p.x), pfma(d.y, t, p.y), pfma(d.z, t, p.z)); }

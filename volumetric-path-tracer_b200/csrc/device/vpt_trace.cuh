@@ -177,7 +177,7 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
     const float l2 = __log2f(psub(1.0f, u));
     if (st.mode == W_DELTA)      st.t = pfma(tc.inv_mult, pmul(tc.inv_max, pmul(l2, -0.693147182f)), st.t);
     else if (st.mode == W_RATIO) st.t = pfma(kp.tr_depth, pmul(tc.sigma_r_inv, pmul(l2, -0.693147182f)), st.t);
-    else st.t = psub(st.t, __fdividef(pmul(kp.tr_depth, pmul(tc.inv_max, pmul(l2, 0.693147182f))), kp.extinction.x));
+    else st.t = pfma(-pmul(pmul(pmul(l2, 0.693147182f), tc.inv_max), kp.tr_depth), 1.0f / kp.extinction.x, st.t);   // fma(-(log*a*b), rcp(ext), t): reference SASS
     if (st.mode != W_EMIT && st.t >= st.distance) { st.op = OP_GLUE; st.exit_reason = EX_DISTANCE; return; }
 
     st.wpos = madd3(st.wpos, st.wdir, st.t);                  // cumulative t, never reset (quirk Q2)

@@ -19,15 +19,15 @@ enum VolPhase : int {
 };
 enum VolTrKind : int { VTR_SUN = 0, VTR_POINT = 1, VTR_SKY_LIGHT = 2, VTR_SKY_BSDF = 3 };
 
-constexpr float kInv4Pi = (float)(1.0f / (4.0f * 3.14159265358979323846));      // isotropic(), :270-275
+constexpr float kInv4Pi = 1.0f / (4.0f * VPT_PI_F);                             // isotropic(), :270-275 (float M_PI)
 
 VPT_DEV float power_heuristic1(float f, float g) { return (f * f) / (f * f + g * g); }   // light.h:65-69 with nf = ng = 1
 
 // equirect HDRI radiance along wi (reference sample_env_tex, :897-907)
 VPT_DEV float3 env_tex_radiance(const vpt_kernel_params& kp, float3 wi) {
     const float4 t = tex2D<float4>((cudaTextureObject_t)kp.env_tex,
-                                   atan2f(wi.z, wi.x) * (float)(0.5 / 3.14159265358979323846) + 0.5f,
-                                   acosf(fmaxf(fminf(wi.y, 1.0f), -1.0f)) * (float)(1.0 / 3.14159265358979323846));
+                                   atan2f(wi.z, wi.x) * (float)(0.5 / VPT_PI_F) + 0.5f,
+                                   acosf(fmaxf(fminf(wi.y, 1.0f), -1.0f)) * (float)(1.0 / VPT_PI_F));
     return f3(t.x, t.y, t.z);
 }
 
@@ -56,7 +56,7 @@ VPT_DEV float env_cdf_sample(const vpt_kernel_params& kp, Rng peek, float3& wo) 
     const float d_cdf_marginal = tex1D<float>(mcdf, (float)(v + 1)) - tex1D<float>(mcdf, (float)v);
     if (d_cdf_marginal > .0f) dv /= d_cdf_marginal;
     const float marginal_pdf = tex1D<float>(mfun, v + dv) / kp.env_marginal_int;
-    const float theta = ((float(v) + dv) / float(res)) * 3.14159265358979323846;
+    const float theta = ((float(v) + dv) / float(res)) * VPT_PI_F;          // the reference's M_PI is the float of helper_math.h:47
 
     first = 0; len = res;
     while (len > 0) {                                              // upper bound of zeta in row v of the conditional cdf
@@ -69,12 +69,13 @@ VPT_DEV float env_cdf_sample(const vpt_kernel_params& kp, Rng peek, float3& wo) 
     const float d_cdf_conditional = tex2D<float>(ccdf, (float)(u + 1), (float)v) - tex2D<float>(ccdf, (float)u, (float)v);
     if (d_cdf_conditional > 0) du /= d_cdf_conditional;
     const float conditional_pdf = tex2D<float>(cfun, u + du, (float)v) / tex1D<float>(mfun, (float)v);
-    const float phi = ((float(u) + du) / float(res)) * 3.14159265358979323846 * 2.0f;
+    const float xphi = (float(u) + du) / float(res);
+    const float phi = pfma(xphi, VPT_PI_F, pmul(xphi, VPT_PI_F));             // (x * pi) * 2 as the reference build evaluates it: x*pi + x*pi, fused
 
     const float cos_theta = cosf(theta), sin_theta = sinf(theta);
     const float sin_phi = sinf(phi), cos_phi = cosf(phi);
     wo = normalize(f3(pmul(sin_theta, cos_phi), pmul(sin_theta, sin_phi), cos_theta));
-    return (marginal_pdf * conditional_pdf) / (2 * 3.14159265358979323846 * 3.14159265358979323846 * sin_theta);
+    return (marginal_pdf * conditional_pdf) / (2 * VPT_PI_F * VPT_PI_F * sin_theta);
 }
 
 // density of direction wi under the tabulated distribution (reference pdf_li + draw_pdf_from_distribution, :1342-1354, :250-262)
@@ -83,9 +84,9 @@ VPT_DEV float env_cdf_pdf(const vpt_kernel_params& kp, float3 wi) {
     const float phi = atan2f(wi.z, wi.x);
     const float sin_theta = sinf(theta);
     if (sin_theta == .0f) return .0f;
-    const float s = 2.0f * 3.14159265358979323846 * 3.14159265358979323846 * sin_theta;
-    const float px = (float)(phi * 1.0f / (2.0f * 3.14159265358979323846)) / s;
-    const float py = (float)(theta * 1.0f / 3.14159265358979323846) / s;
+    const float s = 2.0f * VPT_PI_F * VPT_PI_F * sin_theta;
+    const float px = (phi * 1.0f / (2.0f * VPT_PI_F)) / s;                    // INV_2_PI / INV_PI are unparenthesised float macros (:85-87)
+    const float py = (theta * 1.0f / VPT_PI_F) / s;
     const int res = kp.env_sample_tex_res;
     const int iu = max(0, min(int(px * res), res - 1));
     const int iv = max(0, min(int(py * res), res - 1));
@@ -94,12 +95,12 @@ VPT_DEV float env_cdf_pdf(const vpt_kernel_params& kp, float3 wi) {
     return conditional / marginal;
 }
 
-// uniform direction on the sphere from a COPY of the generator (reference sample_spherical, :293-304; op order from its PTX)
+// uniform direction on the sphere from a COPY of the generator (reference sample_spherical, :293-304; op order and fusion from its SASS)
 VPT_DEV float3 peek_spherical(Rng peek) {
-    const float phi = pmul(peek.next(), (float)(2.0f * 3.14159265358979323846));
+    const float phi = pmul(peek.next(), 2.0f * VPT_PI_F);
     const float u = peek.next();
     const float cos_theta = psub(1.0f, padd(u, u));
-    const float sin_theta = sqrtf(psub(1.0f, pmul(cos_theta, cos_theta)));
+    const float sin_theta = sqrtf(pfma(-cos_theta, cos_theta, 1.0f));          // fused in the reference SASS
     return f3(pmul(sin_theta, cosf(phi)), pmul(sin_theta, sinf(phi)), cos_theta);
 }
 
