@@ -74,7 +74,11 @@ VPT_DEV float env_cdf_sample(const vpt_kernel_params& kp, Rng peek, float3& wo) 
 
     const float cos_theta = cosf(theta), sin_theta = sinf(theta);
     const float sin_phi = sinf(phi), cos_phi = cosf(phi);
-    wo = normalize(f3(pmul(sin_theta, cos_phi), pmul(sin_theta, sin_phi), cos_theta));
+    // normalize(): at this call site the reference build sums the squares in x, y, z order (SASS: FMUL x*x; FFMA y; FFMA z),
+    // unlike the y-first order of its other dot products
+    const float wx = pmul(sin_theta, cos_phi), wy = pmul(sin_theta, sin_phi);
+    const float inv = rsqrtf(pfma(cos_theta, cos_theta, pfma(wy, wy, pmul(wx, wx))));
+    wo = f3(pmul(wx, inv), pmul(wy, inv), pmul(cos_theta, inv));
     return (marginal_pdf * conditional_pdf) / (2 * VPT_PI_F * VPT_PI_F * sin_theta);
 }
 
