@@ -68,6 +68,9 @@ struct PhiloxBlock { uint32_t x, y, z, w; };
 
 // one out-of-line copy: ~60 integer instructions that would otherwise be inlined at every draw site
 __device__ __noinline__ PhiloxBlock philox4x32_10(uint32_t c0, uint32_t c1, uint32_t key0) {
+#ifdef VPT_EXP_CHEAP_RNG   // development experiment only (breaks parity): what would a free generator buy?
+    { PhiloxBlock b; b.x = (c0 ^ key0) * 2654435761u; b.y = b.x * 40503u + c1; b.z = b.y ^ (b.x >> 7); b.w = b.z * 2246822519u; return b; }
+#endif
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
     uint32_t x0 = c0, x1 = c1, x2 = 0u, x3 = 0u, k0 = key0, k1 = 0u;
 #pragma unroll

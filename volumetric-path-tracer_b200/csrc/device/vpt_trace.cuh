@@ -64,6 +64,7 @@ struct PathState {
     bool   mi, first_walk, have_closest, sphere_bounced;
     bool   sphere_free;   // the running walk's line provably misses the sphere: its per-step intersection tests are skipped
     uint32_t lp, pass, qslot;
+    uint32_t packed;      // word 30 as parked (walk path only: the stepping loop edits mode-independent bits in place)
     Rng    rng;
 };
 
@@ -130,34 +131,34 @@ VPT_DEV void load_ray(const PoolView& pv, int s, PathState& st, const FrameArgs&
     ray_rng_init(st, fa, k);
 }
 
-// A walk only touches part of the record: 19 words in, 15 words out instead of 34 each way.
+// A walk only touches part of the record (13 words in, 10 out instead of 34 each way) and only two of the eleven fields packed
+// in word 30: the packed word is carried as is and patched on the way out (unpacking/packing everything cost 5 % of the kernel's
+// instructions).  beta is not carried either: the one event that changes it (a scatter) updates it in place in shared memory.
+constexpr uint32_t kExitMask = 7u << 6;
 VPT_DEV void load_walk(const PoolView& pv, int s, PathState& st, const FrameArgs& fa)
 {
-    st.beta = f3(pv.f(9, s), pv.f(10, s), pv.f(11, s));
     st.wpos = f3(pv.f(12, s), pv.f(13, s), pv.f(14, s)); st.wdir = f3(pv.f(15, s), pv.f(16, s), pv.f(17, s));
     st.aux = f3(pv.f(18, s), pv.f(19, s), pv.f(20, s));
     st.alpha = pv.f(21, s); st.t = pv.f(23, s); st.distance = pv.f(24, s); st.trv = pv.f(25, s);
     const uint32_t k = pv.u(28, s); st.lp = pv.u(29, s);
     const uint32_t a = pv.u(30, s);
-    st.phase = a & 15; st.mode = (a >> 4) & 3; st.exit_reason = (a >> 6) & 7; st.tr_kind = (a >> 9) & 3; st.obj_c = (a >> 11) & 3;
-    st.mi = (a >> 13) & 1; st.first_walk = (a >> 14) & 1; st.have_closest = (a >> 15) & 1; st.sphere_bounced = (a >> 16) & 1; st.sphere_free = (a >> 17) & 1; st.pass = a >> 18;
+    st.packed = a;
+    st.mode = (a >> 4) & 3; st.exit_reason = (a >> 6) & 7; st.sphere_free = (a >> 17) & 1; st.pass = a >> 18;
     ray_rng_init(st, fa, k);
 }
 
 VPT_DEV void store_walk(const PoolView& pv, int s, const PathState& st)
 {
-    pv.f(9, s) = st.beta.x; pv.f(10, s) = st.beta.y; pv.f(11, s) = st.beta.z;
     pv.f(12, s) = st.wpos.x; pv.f(13, s) = st.wpos.y; pv.f(14, s) = st.wpos.z;
     pv.f(18, s) = st.aux.x; pv.f(19, s) = st.aux.y; pv.f(20, s) = st.aux.z;
-    pv.f(21, s) = st.alpha; pv.f(23, s) = st.t; pv.f(24, s) = st.distance; pv.f(25, s) = st.trv;
+    pv.f(21, s) = st.alpha; pv.f(23, s) = st.t; pv.f(25, s) = st.trv;
     pv.u(28, s) = st.rng.k;
-    pv.u(30, s) = (uint32_t)st.phase | ((uint32_t)st.mode << 4) | ((uint32_t)st.exit_reason << 6) | ((uint32_t)st.tr_kind << 9) |
-                  ((uint32_t)st.obj_c << 11) | ((uint32_t)st.mi << 13) | ((uint32_t)st.first_walk << 14) | ((uint32_t)st.have_closest << 15) |
-                  ((uint32_t)st.sphere_bounced << 16) | ((uint32_t)st.sphere_free << 17) | (st.pass << 18);
+    pv.u(30, s) = (st.packed & ~kExitMask) | ((uint32_t)st.exit_reason << 6);
 }
 
 // ---- OP_STEP -------------------------------------------------------------------------------------------------
-VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph, uint32_t& nlook)
+VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph, uint32_t& nlook,
+                       const PoolView& pv, int slot)
 {
     const SceneTables& sc = fs.sc;
     const vpt_kernel_params& kp = fa.kp;
@@ -195,7 +196,9 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
         const float3 density_color = reinterpret_cast<const float3*>(kp.density_color_texture)[index];
         if (st.alpha < 1.0f) st.alpha += density;
         if (pmul(tc.inv_max, density) > st.rng.next()) {
-            st.beta *= (ld3(kp.albedo) * Cd * density_color / ld3(kp.extinction)) * float(kp.energy_inject);
+            float3 beta = f3(pv.f(9, slot), pv.f(10, slot), pv.f(11, slot));     // the path's throughput lives in the parked record
+            beta *= (ld3(kp.albedo) * Cd * density_color / ld3(kp.extinction)) * float(kp.energy_inject);
+            pv.f(9, slot) = beta.x; pv.f(10, slot) = beta.y; pv.f(11, slot) = beta.z;
             st.op = OP_GLUE; st.exit_reason = EX_SCATTER;
         }
     } else {
@@ -529,7 +532,7 @@ k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atm
                     break;
                 }
                 if (cur >= 0) {
-                    walk_step(st, fs, fa, tc, sph, nlook); lane_steps++;
+                    walk_step(st, fs, fa, tc, sph, nlook, pv, cur); lane_steps++;
                     if (st.op != OP_STEP) {                        // walk ended: park the ray with its new tag
                         store_walk(pv, cur, st);
                         if (cur == 0) tag0 = st.op; else if (cur == 1) tag1 = st.op; else tag2 = st.op;
