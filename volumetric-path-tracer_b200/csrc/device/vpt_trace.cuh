@@ -191,11 +191,12 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
     }
     const float density = leaf_density(sc, fs.vol0, leaf, st.wpos);
     if (st.mode == W_DELTA) {
-        const float3 Cd = leaf_color(sc, fs.vol0, leaf, st.wpos);
-        const int index = int(floorf(fminf(fmaxf((density * tc.inv_max * 255.0f / kp.emission_pivot), 0.0f), 255.0f)));
-        const float3 density_color = reinterpret_cast<const float3*>(kp.density_color_texture)[index];
         if (st.alpha < 1.0f) st.alpha += density;
         if (pmul(tc.inv_max, density) > st.rng.next()) {
+            // colour terms are only consumed by an accepted collision: the reference evaluates them at every step and drops them
+            const float3 Cd = leaf_color(sc, fs.vol0, leaf, st.wpos);
+            const int index = int(floorf(fminf(fmaxf((density * tc.inv_max * 255.0f / kp.emission_pivot), 0.0f), 255.0f)));
+            const float3 density_color = reinterpret_cast<const float3*>(kp.density_color_texture)[index];
             float3 beta = f3(pv.f(9, slot), pv.f(10, slot), pv.f(11, slot));     // the path's throughput lives in the parked record
             beta *= (ld3(kp.albedo) * Cd * density_color / ld3(kp.extinction)) * float(kp.energy_inject);
             pv.f(9, slot) = beta.x; pv.f(10, slot) = beta.y; pv.f(11, slot) = beta.z;
