@@ -265,7 +265,7 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if tj.get("passes_per_launch") == opts.get("passes_per_chunk", 16) and world == 1: traffic = tj["k_trace_dram_bytes_per_launch"]
+            if tj.get("passes_per_launch") == opts.get("passes_per_chunk", 32) and world == 1: traffic = tj["k_trace_dram_bytes_per_launch"]
         bytes_per_sample = 88.0 + 32.0 * lookups_per_sample          # framebuffer stream + 32 B per density lookup
         step_gbs = value * bytes_per_sample / 1e3
         roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -284,7 +284,7 @@ def main():
         cpu_base = cpu_baseline_sample(V, scene, r.cam, kp)
 
     if rank == 0:
-        config.update({"passes_per_chunk": opts.get("passes_per_chunk", 16), "partition": f"{world} rank(s), interleaved 8-row stripes" if world > 1 else "single GPU",
+        config.update({"passes_per_chunk": opts.get("passes_per_chunk", 32), "partition": f"{world} rank(s), interleaved 8-row stripes" if world > 1 else "single GPU",
                        "collective": "1 NCCL all_gather_into_tensor of float3 accumulators per step" if world > 1 else "none"})
         line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",

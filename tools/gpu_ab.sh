@@ -2,7 +2,7 @@
 # A/B of library variants: tools/gpu_ab.sh libA.so libB.so ...   (first: parity run of the default library)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-echo "== parity (default lib)"; timeout 900 python -m pytest tests -m gpu -x -q -k "golden or live or fused or partition or point_lights" 2>&1 | tail -3
+echo "== parity (${PARITY_LIB:-default lib})"; VPT_LIB_NAME=${PARITY_LIB:-libvpt_b200.so} timeout 900 python -m pytest tests -m gpu -x -q -k "golden or live or fused or partition or point_lights" 2>&1 | tail -3
 for lib in "$@"; do
 echo "== $lib"; VPT_LIB_NAME=$lib timeout 900 python bench.py --steps 6 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import sys, json

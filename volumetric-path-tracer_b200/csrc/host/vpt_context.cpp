@@ -37,7 +37,7 @@ struct vpt_context {
     int num_sms = 0;
     std::string err;
     // options
-    int passes_per_chunk = 16;
+    int passes_per_chunk = 32;
     int ctas_per_sm = 0;
     // partition
     int rank = 0, n_ranks = 1, stripe_rows = 16;
