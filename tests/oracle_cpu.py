@@ -127,7 +127,7 @@ def timed_sample(scene, cam, kp, width, height, seconds_target=12.0):
     k.resolution = V.u2(width, height)
     cores = os.cpu_count() or 1
     # centre tile (dense part of the image), grown until the sample takes long enough
-    tw, th, spp = 480, 270, 1
+    tw, th, spp = 1280, 720, 1
     rect = ((width - tw) // 2, (height - th) // 2, (width + tw) // 2, (height + th) // 2)
     t0 = time.perf_counter(); orc.render(cam, k, spp, rect=rect); dt = time.perf_counter() - t0
     reps = max(1, min(64, int(seconds_target / max(dt, 1e-3))))
