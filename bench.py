@@ -248,7 +248,11 @@ def main():
             peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
         r.set_option("profile", 1); r.set_option("count_stats", 1)
         r.counters(reset=True); r.kernel_times()
-        for _ in range(2): step()
+        def render_only():                                  # rank-local work only: no collective here, the other ranks have moved on
+            r.kp.iteration = 0
+            r.render(SPP, stream=stream)
+        for _ in range(2): render_only()
+        torch.cuda.synchronize()
         kt = r.kernel_times(); cnt = r.counters()
         r.set_option("profile", 0); r.set_option("count_stats", 0)
         n_steps_prof = 2
