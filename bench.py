@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="passes fused per kernel round (0 = library default)")
     ap.add_argument("--sched-min-lanes", type=int, default=0, help="trace scheduler threshold (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--generic-kernel", action="store_true", help="A/B: force the generic trace kernel instantiation")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -197,6 +198,7 @@ def main():
     opts = {}
     if args.chunk: opts["passes_per_chunk"] = args.chunk
     if args.sched_min_lanes: opts["sched_min_lanes"] = args.sched_min_lanes
+    if args.generic_kernel: opts["generic_kernel"] = 1
     stream = torch.cuda.current_stream().cuda_stream
     if world > 1:
         dr = V.DistributedRenderer(scene, WIDTH, HEIGHT, kp=kp, stripe_rows=8, options=opts)

@@ -310,6 +310,17 @@ def test_fused_passes_equal_single_passes_bitwise_full_hd(dragon):
     assert float(a.buffers.accum.mean()) > 1e-3 and bool(torch.isfinite(a.buffers.accum).all())
 
 
+def test_lean_and_generic_trace_kernels_agree_bitwise(dragon):
+    """The host picks a trace-kernel instantiation without multi-volume / emission / point-light code when none is in play."""
+    scene = make_scene(dragon)
+    a = V.Renderer(scene, 640, 360, kp=make_kp(ray_depth=100))
+    b = V.Renderer(scene, 640, 360, kp=make_kp(ray_depth=100), options={"generic_kernel": 1})
+    scene.reset_blue_noise(); a.render(4); torch.cuda.synchronize()
+    scene.reset_blue_noise(); b.render(4); torch.cuda.synchronize()
+    for name in ("accum", "depth", "raw", "display"):
+        assert torch.equal(getattr(a.buffers, name), getattr(b.buffers, name)), name
+
+
 def test_partition_invariance_and_determinism(dragon):
     """Rendering the frame as 4 interleaved-stripe shards and un-permuting reproduces the single-rank frame
     bit for bit (global pixel index keys the RNG), whatever the scheduling options."""

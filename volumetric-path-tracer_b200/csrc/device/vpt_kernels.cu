@@ -471,32 +471,41 @@ cudaError_t launch_generate(const FrameArgs& fa, int n_passes, cudaStream_t s)
 
 static size_t trace_smem_bytes() { return (size_t)kTraceWarps * kRayWords * kPool * sizeof(float); }
 
-// atm != null selects the volumetric path integrator variant (Kernel_params.integrator != 0)
-cudaError_t launch_trace(const FrameArgs& fa, const vpt_atmosphere* atm, int n_ctas, cudaStream_t s)
+// atm != null selects the volumetric path integrator variant (Kernel_params.integrator != 0); lean selects the instantiation
+// without multi-volume lists, emission walk and point lights (the caller guarantees none of them is in play)
+template <int kInteg, bool kLean>
+static cudaError_t launch_trace_t(const FrameArgs& fa, const vpt_atmosphere* atm, int n_ctas, cudaStream_t s)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_trace<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
+        cudaError_t e = cudaFuncSetAttribute(k_trace<kInteg, kLean>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if (atm) k_trace<1><<<n_ctas, kTraceThreads, trace_smem_bytes(), s>>>(fa, *atm);
-    else     k_trace<0><<<n_ctas, kTraceThreads, trace_smem_bytes(), s>>>(fa, NoAtmo{});
+    if constexpr (kInteg != 0) k_trace<kInteg, kLean><<<n_ctas, kTraceThreads, trace_smem_bytes(), s>>>(fa, *atm);
+    else                       k_trace<kInteg, kLean><<<n_ctas, kTraceThreads, trace_smem_bytes(), s>>>(fa, NoAtmo{});
     return cudaGetLastError();
 }
 
-int trace_max_ctas_per_sm(int integrator)
+cudaError_t launch_trace(const FrameArgs& fa, const vpt_atmosphere* atm, bool lean, int n_ctas, cudaStream_t s)
+{
+    if (atm) return launch_trace_t<1, false>(fa, atm, n_ctas, s);
+    return lean ? launch_trace_t<0, true>(fa, nullptr, n_ctas, s) : launch_trace_t<0, false>(fa, nullptr, n_ctas, s);
+}
+
+template <int kInteg, bool kLean>
+static int max_ctas_t()
 {
     int n = 0;
-    if (integrator) {
-        cudaFuncSetAttribute(k_trace<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<1>, kTraceThreads, trace_smem_bytes());
-    } else {
-        cudaFuncSetAttribute(k_trace<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<0>, kTraceThreads, trace_smem_bytes());
-    }
+    cudaFuncSetAttribute(k_trace<kInteg, kLean>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<kInteg, kLean>, kTraceThreads, trace_smem_bytes());
     return n;
+}
+
+int trace_max_ctas_per_sm(int integrator, bool lean)
+{
+    if (integrator) return max_ctas_t<1, false>();
+    return lean ? max_ctas_t<0, true>() : max_ctas_t<0, false>();
 }
 
 cudaError_t launch_resolve(const FrameArgs& fa, const vpt_atmosphere* sky, int n_passes, int sampled, int write_display, cudaStream_t s)

@@ -157,6 +157,9 @@ VPT_DEV void store_walk(const PoolView& pv, int s, const PathState& st)
 }
 
 // ---- OP_STEP -------------------------------------------------------------------------------------------------
+// kLean: single volume, no emission walk, no point lights -- the headline configuration; those features' code is compiled out
+// of that instantiation (smaller hot loop: the kernel is fetch-stall bound)
+template <bool kLean>
 VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph, uint32_t& nlook,
                        const PoolView& pv, int slot)
 {
@@ -177,24 +180,24 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
     // t -= log(1-u) * a * b, as the reference build evaluates it: fma(b, a * (lg2(1-u) * -ln2), t)
     const float l2 = __log2f(psub(1.0f, u));
     if (st.mode == W_DELTA)      st.t = pfma(tc.inv_mult, pmul(tc.inv_max, pmul(l2, -0.693147182f)), st.t);
-    else if (st.mode == W_RATIO) st.t = pfma(kp.tr_depth, pmul(tc.sigma_r_inv, pmul(l2, -0.693147182f)), st.t);
+    else if (kLean || st.mode == W_RATIO) st.t = pfma(kp.tr_depth, pmul(tc.sigma_r_inv, pmul(l2, -0.693147182f)), st.t);
     else st.t = pfma(-pmul(pmul(pmul(l2, 0.693147182f), tc.inv_max), kp.tr_depth), 1.0f / kp.extinction.x, st.t);   // fma(-(log*a*b), rcp(ext), t): reference SASS
-    if (st.mode != W_EMIT && st.t >= st.distance) { st.op = OP_GLUE; st.exit_reason = EX_DISTANCE; return; }
+    if ((kLean || st.mode != W_EMIT) && st.t >= st.distance) { st.op = OP_GLUE; st.exit_reason = EX_DISTANCE; return; }
 
     st.wpos = madd3(st.wpos, st.wdir, st.t);                  // cumulative t, never reset (quirk Q2)
     if (!aabb_contains(sc.root_pmin, sc.root_pmax, st.wpos)) { st.op = OP_GLUE; st.exit_reason = EX_OUTSIDE; return; }
 
     nlook++;
-    if (st.mode == W_EMIT) {
+    if (!kLean && st.mode == W_EMIT) {
         st.aux += leaf_emission(sc, fs.vol0, leaf, st.wpos, reinterpret_cast<const float3*>(kp.emission_texture), kp.emission_pivot, kp.emission_scale);
         return;
     }
-    const float density = leaf_density(sc, fs.vol0, leaf, st.wpos);
+    const float density = kLean ? 0.0f + volume_density(fs.vol0, st.wpos) : leaf_density(sc, fs.vol0, leaf, st.wpos);
     if (st.mode == W_DELTA) {
         if (st.alpha < 1.0f) st.alpha += density;
         if (pmul(tc.inv_max, density) > st.rng.next()) {
             // colour terms are only consumed by an accepted collision: the reference evaluates them at every step and drops them
-            const float3 Cd = leaf_color(sc, fs.vol0, leaf, st.wpos);
+            const float3 Cd = kLean ? fmax3(f3(0.0f), volume_color(fs.vol0, st.wpos)) : leaf_color(sc, fs.vol0, leaf, st.wpos);
             const int index = int(floorf(fminf(fmaxf((density * tc.inv_max * 255.0f / kp.emission_pivot), 0.0f), 255.0f)));
             const float3 density_color = reinterpret_cast<const float3*>(kp.density_color_texture)[index];
             float3 beta = f3(pv.f(9, slot), pv.f(10, slot), pv.f(11, slot));     // the path's throughput lives in the parked record
@@ -231,6 +234,7 @@ VPT_DEV void begin_ratio_walk(PathState& st, const FrameShared& fs, const TraceC
 VPT_DEV float finish_ratio_walk(const PathState& st) { return clampf(st.trv * st.T_c, .0f, 1.0f); }
 
 // ---- the integrator's control flow between heavy operations -------------------------------------------------
+template <bool kLean>
 VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph)
 {
     const SceneTables& sc = fs.sc;
@@ -303,9 +307,9 @@ VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, 
                 const float phase_pdf = hg_phase(cos_theta, kp.phase_g1);
                 const float3 Ld = f3(tr) * phase_pdf;
                 st.L += Ld * ld3(kp.sun_color) * kp.sun_mult * st.beta;
-                if (fa.lights.num_lights > 0) { st.aux = f3(.0f); st.light_budget = 10; st.phase = PH_POINT_NEXT; }
+                if (!kLean && fa.lights.num_lights > 0) { st.aux = f3(.0f); st.light_budget = 10; st.phase = PH_POINT_NEXT; }
                 else st.phase = PH_EMISSION;
-            } else if (st.tr_kind == TR_POINT) {                    // reference point_light::Le, light.h:104-121
+            } else if (!kLean && st.tr_kind == TR_POINT) {                    // reference point_light::Le, light.h:104-121
                 if (st.light_budget < (int)fa.lights.num_lights) {
                     const vpt_point_light& pl = reinterpret_cast<const vpt_point_light*>(fa.lights.light_ptr)[st.light_index];
                     const float3 lpos = ld3(pl.pos);
@@ -328,6 +332,7 @@ VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, 
             break;
         }
         case PH_POINT_NEXT: {                                       // reference estimate_point_light (:1445-1475)
+            if (kLean) { st.phase = PH_EMISSION; break; }
             if (st.light_budget < 0) { st.L += st.aux * st.beta; st.phase = PH_EMISSION; break; }
             const vpt_point_light* lp = reinterpret_cast<const vpt_point_light*>(fa.lights.light_ptr);
             st.light_index = int(floorf(st.rng.next() * fa.lights.num_lights));
@@ -336,7 +341,7 @@ VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, 
             return;
         }
         case PH_EMISSION:
-            if (kp.emission_scale > 0 && st.mi) {
+            if (!kLean && kp.emission_scale > 0 && st.mi) {
                 st.wpos = st.pos; st.wdir = st.dir; st.t = 0.0f; st.aux = f3(.0f);
                 st.mode = W_EMIT; st.op = OP_STEP; st.phase = PH_AFTER_EMIT;
                 return;
@@ -412,7 +417,7 @@ VPT_DEV void write_sample(const PathState& st, const FrameArgs& fa)
 // caller's AtmosphereParameters in the kernel (sky radiance decides whether a transmittance walk is run at all)
 struct NoAtmo { int pad[4]; };
 
-template <int kInteg>
+template <int kInteg, bool kLean>
 __global__ void __launch_bounds__(kTraceThreads, kTraceMinCtas)
 k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atmosphere, NoAtmo>::type atm)
 {
@@ -504,7 +509,7 @@ k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atm
                 }
                 if (st.op == OP_GLUE) {
                     if constexpr (kInteg != 0) advance_vol(st, fs, fa, atm, tc, sph);
-                    else advance(st, fs, fa, tc, sph);
+                    else advance<kLean>(st, fs, fa, tc, sph);
                 }
                 if (st.op == OP_TRBEGIN) begin_ratio_walk(st, fs, tc, sph);
                 if (st.op == OP_FINISH) { write_sample<kInteg>(st, fa); st.op = OP_IDLE; }
@@ -533,7 +538,7 @@ k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atm
                     break;
                 }
                 if (cur >= 0) {
-                    walk_step(st, fs, fa, tc, sph, nlook, pv, cur); lane_steps++;
+                    walk_step<kLean>(st, fs, fa, tc, sph, nlook, pv, cur); lane_steps++;
                     if (st.op != OP_STEP) {                        // walk ended: park the ray with its new tag
                         store_walk(pv, cur, st);
                         if (cur == 0) tag0 = st.op; else if (cur == 1) tag1 = st.op; else tag2 = st.op;

@@ -43,6 +43,8 @@ struct vpt_context {
     int rank = 0, n_ranks = 1, stripe_rows = 16;
     // scene cache
     vpt_devptr_t cached_volumes = 0, cached_root = 0;
+    bool   scene_single_volume = false;
+    int    force_generic = 0;        // option "generic_kernel": 1 = never use the lean trace instantiation (A/B and tests)
     vpt::SceneTables* d_scene = nullptr;
     vpt::OctInternal* d_internal = nullptr;
     uint2* d_leaf_list = nullptr;
@@ -145,6 +147,7 @@ int vpt_set_option(vpt_context* c, const char* key, int value) {
     else if (k == "ctas_per_sm") { if (value < 0 || value > 8) return fail(c, VPT_ERR_INVALID, "ctas_per_sm must be 0..8"); c->ctas_per_sm = value; }
     else if (k == "sched_min_lanes") { if (value < 1 || value > 32) return fail(c, VPT_ERR_INVALID, "sched_min_lanes must be 1..32"); c->sched_min_lanes = value; }
     else if (k == "debug_flags") { c->debug_flags = value; }
+    else if (k == "generic_kernel") { c->force_generic = value ? 1 : 0; }
     else if (k == "count_stats") { c->count_stats = value ? 1 : 0; }
     else if (k == "profile") { c->profile = value ? 1 : 0; }
     else return fail(c, VPT_ERR_INVALID, "unknown option " + k);
@@ -246,7 +249,15 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
                                               c->d_scene, c->d_internal, c->d_leaf_list, c->d_leaf_indices, c->d_vrec, VPT_OCT_MAX_VOLUMES, stream));
         c->launches++;
         c->cached_volumes = d_volumes; c->cached_root = d_root;
+        // one 4-byte read-back per scene: lets the host pick the trace kernel instantiation without the multi-volume code
+        int single = 0;
+        VPT_CUDA(c, cudaMemcpyAsync(&single, reinterpret_cast<const char*>(c->d_scene) + offsetof(vpt::SceneTables, single_volume), sizeof(int),
+                                    cudaMemcpyDeviceToHost, stream));
+        VPT_CUDA(c, cudaStreamSynchronize(stream));
+        c->scene_single_volume = single != 0;
     }
+    // "lean" = nothing but one volume, sun and environment in play (the headline configuration)
+    const bool lean = c->scene_single_volume && !(kp.emission_scale > 0.0f) && fa.lights.num_lights == 0 && kp.integrator == 0 && !c->force_generic;
 
     fa.sphere = reinterpret_cast<const vpt_sphere*>(d_sphere);
     fa.scene = c->d_scene;
@@ -276,7 +287,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
     fa.queue_count = c->d_counters; fa.queue_head = c->d_counters + 1;
     fa.planeA = c->d_planeA; fa.planeB = c->d_planeB; fa.planeC = c->d_planeC; fa.planeD = planeD ? c->d_planeD : nullptr;
 
-    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : vpt::trace_max_ctas_per_sm(vol_integ ? 1 : 0);
+    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : vpt::trace_max_ctas_per_sm(vol_integ ? 1 : 0, lean);
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int trace_ctas = c->num_sms * ctas_per_sm;
 
@@ -299,7 +310,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         VPT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned) * 2, stream));
         VPT_CUDA(c, timed(3, [&] { return vpt::launch_bn_prepare((void*)kp.blue_noise_buffer, c->d_bn_table, (int)np, stream); }));   // jitter table + advance
         VPT_CUDA(c, timed(0, [&] { return vpt::launch_generate(fa, (int)np, stream); }));
-        VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, vol_integ ? &atmo : nullptr, trace_ctas, stream); }));
+        VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, vol_integ ? &atmo : nullptr, lean, trace_ctas, stream); }));
         const bool last = (done + np == n_passes);
         VPT_CUDA(c, timed(2, [&] { return vpt::launch_resolve(fa, sky, (int)np, 1, last ? 1 : 0, stream); }));
         c->launches += 4;
