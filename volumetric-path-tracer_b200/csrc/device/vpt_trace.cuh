@@ -187,7 +187,7 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
     st.wpos = madd3(st.wpos, st.wdir, st.t);                  // cumulative t, never reset (quirk Q2)
     if (!aabb_contains(sc.root_pmin, sc.root_pmax, st.wpos)) { st.op = OP_GLUE; st.exit_reason = EX_OUTSIDE; return; }
 
-    if (!kLean) nlook++;                                         // statistics are kept by the generic instantiation only
+    nlook++;
     if (!kLean && st.mode == W_EMIT) {
         st.aux += leaf_emission(sc, fs.vol0, leaf, st.wpos, reinterpret_cast<const float3*>(kp.emission_texture), kp.emission_pivot, kp.emission_scale);
         return;
@@ -482,7 +482,7 @@ k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atm
                 }
                 store_ray(pv, j, st);
                 if (j == 0) tag0 = st.op; else if (j == 1) tag1 = st.op; else tag2 = st.op;
-                if (!kLean) lane_rays++;
+                lane_rays++;
             }
         }
 
@@ -515,9 +515,9 @@ k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atm
                 if (st.op == OP_FINISH) { write_sample<kInteg>(st, fa); st.op = OP_IDLE; }
                 else store_ray(pv, j, st);
                 if (j == 0) tag0 = st.op; else if (j == 1) tag1 = st.op; else tag2 = st.op;
-                if (!kLean) lane_ops++;
+                lane_ops++;
             }
-            if (!kLean) warp_ops++;
+            warp_ops++;
             continue;
         }
 
@@ -538,7 +538,7 @@ k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atm
                     break;
                 }
                 if (cur >= 0) {
-                    walk_step<kLean>(st, fs, fa, tc, sph, nlook, pv, cur); if (!kLean) lane_steps++;
+                    walk_step<kLean>(st, fs, fa, tc, sph, nlook, pv, cur); lane_steps++;
                     if (st.op != OP_STEP) {                        // walk ended: park the ray with its new tag
                         store_walk(pv, cur, st);
                         if (cur == 0) tag0 = st.op; else if (cur == 1) tag1 = st.op; else tag2 = st.op;
@@ -546,12 +546,12 @@ k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atm
                     }
                 }
                 parked_lanes = __popc(__ballot_sync(0xffffffffu, ((tag0 != OP_STEP) & (tag0 != OP_IDLE)) | ((tag1 != OP_STEP) & (tag1 != OP_IDLE)) | ((tag2 != OP_STEP) & (tag2 != OP_IDLE) & (tag2 != OP_NOSLOT))));
-                if (!kLean) warp_iters++;
+                warp_iters++;
             }
         }
     }
 
-    if (!kLean && fa.counters) {                              // optional statistics (one atomic set per warp)
+    if (fa.counters) {                                        // optional statistics (one atomic set per warp)
         unsigned long long a = nlook, b = lane_steps, c = lane_ops, d = lane_rays;
         for (int o = 16; o > 0; o >>= 1) {
             a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o); d += __shfl_xor_sync(0xffffffffu, d, o);

@@ -257,7 +257,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         c->scene_single_volume = single != 0;
     }
     // "lean" = nothing but one volume, sun and environment in play (the headline configuration)
-    const bool lean = c->scene_single_volume && !(kp.emission_scale > 0.0f) && fa.lights.num_lights == 0 && kp.integrator == 0 && !c->force_generic && !c->count_stats;   // statistics are counted by the generic instantiation
+    const bool lean = c->scene_single_volume && !(kp.emission_scale > 0.0f) && fa.lights.num_lights == 0 && kp.integrator == 0 && !c->force_generic;
 
     fa.sphere = reinterpret_cast<const vpt_sphere*>(d_sphere);
     fa.scene = c->d_scene;
