@@ -45,7 +45,7 @@ const char* vpt_version(void);
 int  vpt_abi_sizes(size_t* out, int n);
 
 /* Tunables: "passes_per_chunk" (1..64, passes fused per generate/trace/resolve round, default 32),
- * "sched_min_lanes" (1..32, lanes an operation must gather in a warp before it pre-empts stepping, default 8),
+ * "sched_min_lanes" (1..32, lanes an operation must gather in a warp before it pre-empts stepping, default 20),
  * "ctas_per_sm" (0 = occupancy maximum), "count_stats" / "profile" (0|1, see vpt_get_counters / vpt_get_kernel_times). */
 int  vpt_set_option(vpt_context* ctx, const char* key, int value);
 
