@@ -118,6 +118,18 @@ int  vpt_bmp_load_rbg(const char* path, float** xyz_out, int* width, int* height
 int  vpt_exr_load_rgb(const char* path, float** rgb_out, int* width, int* height);          /* fileIO.cpp:356-390 */
 void vpt_free(void* p);
 
+/* Scene / light instance file (.ins) reader -- the text format of read_instance_file, main.cpp:980-1040, SURVEY 8(f) N4:
+ *     "light" \n N \n { px py pz r g b power } x N                                  (point lights)
+ *     N_vdbs \n { vdb_path \n N_inst \n { px py pz qx qy qz qw scale } x N_inst } x N_vdbs   (instanced volumes)
+ * One record per line, whitespace separated, paths taken verbatim (the reference resolves them against its CWD).
+ * *out is one malloc'd block (free with vpt_free): the header below, then n_files vpt_ins_file_entry, then n_records records
+ * of 8 doubles each (volumes: px py pz qx qy qz qw scale; lights: px py pz r g b power 0).  Unlike the reference, a line
+ * with too few numbers is an error (VPT_ERR_IO) instead of leaving the fields uninitialised.  The instance transform itself
+ * (mat4 algebra of main.cpp:1059-1099) is applied by the caller; see volumetric-path-tracer_b200/scene.py:instance_xform. */
+typedef struct vpt_ins_header { int32_t kind; int32_t n_files; int32_t n_records; int32_t reserved; } vpt_ins_header;   /* kind: 0 volumes, 1 lights */
+typedef struct vpt_ins_file_entry { char path[1024]; int32_t first_record; int32_t n_instances; } vpt_ins_file_entry;
+int  vpt_ins_load(const char* path, vpt_ins_header** out);
+
 /* Depth-3 octree over instance bounds in the reference's own node layout (bvh_builder.cpp:61-96 +
  * bvh_kernels.cu:204-246), built in parallel (one thread per node, no device heap, no 600-volume
  * overflow: n > VPT_OCT_MAX_VOLUMES is rejected).  h_volumes: host array of n GPU_VDB.

@@ -74,3 +74,34 @@ def test_hdr_rgbe_rule(tmp_path):
     if hdr:
         big = load_hdr(hdr)
         assert big.shape == (1500, 3000, 4) and abs(float(big[..., :3].mean()) - 0.245057) < 1e-4
+
+
+def test_ins_scene_file_reader(tmp_path):
+    """`.ins` grammar of the reference's read_instance_file (main.cpp:980-1040): volumes form."""
+    from vpt_b200.scene import load_ins
+    p = tmp_path / "two.ins"
+    p.write_text("2\n./assets/dragon.vdb\n3\n0 0 0 0 0 0 1 1\n1.5 -2 3e0 0.0 0.7071068 0 0.7071068 0.5\n-4 5 6 1 0 0 0 2\r\n"
+                 "clouds/cumulus 01.vdb\n1\n10 20 30 0 0 0 1 0.25\n")
+    d = load_ins(str(p))
+    assert d["kind"] == "volumes" and [f["path"] for f in d["files"]] == ["./assets/dragon.vdb", "clouds/cumulus 01.vdb"]
+    assert [len(f["instances"]) for f in d["files"]] == [3, 1]
+    pos, quat, scale = d["files"][0]["instances"][1]
+    assert pos == (1.5, -2.0, 3.0) and quat == (0.0, 0.7071068, 0.0, 0.7071068) and scale == 0.5
+    assert d["files"][1]["instances"][0] == ((10.0, 20.0, 30.0), (0.0, 0.0, 0.0, 1.0), 0.25)
+
+
+def test_ins_light_file_reader_and_errors(tmp_path):
+    from vpt_b200.scene import load_ins
+    p = tmp_path / "lights.ins"
+    p.write_text("light\n2\n9 6 2 1 0.8 0.6 40\n-2 3 8 0.5 0.7 1 25\n")
+    d = load_ins(str(p))
+    assert d == {"kind": "lights", "lights": [((9.0, 6.0, 2.0), (1.0, 0.8, 0.6), 40.0), ((-2.0, 3.0, 8.0), (0.5, 0.7, 1.0), 25.0)]}
+    bad = tmp_path / "short.ins"
+    bad.write_text("1\nfoo.vdb\n2\n0 0 0 0 0 0 1 1\n1 2 3\n")                 # second record has too few numbers
+    with pytest.raises(V.VptError, match="8 numbers"):
+        load_ins(str(bad))
+    with pytest.raises(V.VptError, match="cannot open"):
+        load_ins(str(tmp_path / "missing.ins"))
+    empty = tmp_path / "empty.ins"; empty.write_text("")
+    with pytest.raises(V.VptError, match="empty file"):
+        load_ins(str(empty))

@@ -20,6 +20,7 @@
 #include <cstring>
 #include <fstream>
 #include <iterator>
+#include <sstream>
 #include <string>
 #include <algorithm>
 #include <vector>
@@ -455,6 +456,59 @@ int vpt_texture_destroy(vpt_tex_t tex, void* array) {
 }
 
 void vpt_free(void* p) { free(p); }
+
+int vpt_ins_load(const char* path, vpt_ins_header** out) {
+    if (!path || !out) return fail(nullptr, VPT_ERR_INVALID, "vpt_ins_load: null argument");
+    *out = nullptr;
+    std::ifstream f(path);
+    if (!f) return fail(nullptr, VPT_ERR_IO, std::string("vpt_ins_load: cannot open ") + path);
+    auto bad = [&](const std::string& what) { return fail(nullptr, VPT_ERR_IO, std::string("vpt_ins_load: ") + path + ": " + what); };
+    auto numbers = [](const std::string& line, double* v, int n) { std::istringstream is(line); for (int i = 0; i < n; ++i) if (!(is >> v[i])) return false; return true; };
+    std::string line;
+    if (!std::getline(f, line)) return bad("empty file");
+    while (!line.empty() && (line.back() == '\r' || line.back() == ' ' || line.back() == '\t')) line.pop_back();
+    std::vector<vpt_ins_file_entry> files;
+    std::vector<double> recs;
+    int kind = 0;
+    if (line == "light") {
+        kind = 1;
+        double n = 0;
+        if (!std::getline(f, line) || !numbers(line, &n, 1) || n < 0 || n > 1e7) return bad("light count missing");
+        for (int i = 0; i < (int)n; ++i) {
+            double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (!std::getline(f, line) || !numbers(line, v, 7)) return bad("light record " + std::to_string(i) + " needs 7 numbers: px py pz r g b power");
+            recs.insert(recs.end(), v, v + 8);
+        }
+    } else {
+        double n = 0;
+        if (!numbers(line, &n, 1) || n < 0 || n > 1e6) return bad("first line must be \"light\" or the number of .vdb entries");
+        for (int i = 0; i < (int)n; ++i) {
+            vpt_ins_file_entry e; memset(&e, 0, sizeof(e));
+            if (!std::getline(f, line)) return bad("missing .vdb path of entry " + std::to_string(i));
+            while (!line.empty() && (line.back() == '\r')) line.pop_back();
+            if (line.size() >= sizeof(e.path)) return bad("path too long");
+            memcpy(e.path, line.c_str(), line.size());
+            double cnt = 0;
+            if (!std::getline(f, line) || !numbers(line, &cnt, 1) || cnt < 0 || cnt > 1e7) return bad("missing instance count of entry " + std::to_string(i));
+            e.first_record = (int32_t)(recs.size() / 8); e.n_instances = (int32_t)cnt;
+            for (int x = 0; x < (int)cnt; ++x) {
+                double v[8];
+                if (!std::getline(f, line) || !numbers(line, v, 8)) return bad("instance " + std::to_string(x) + " of entry " + std::to_string(i) + " needs 8 numbers: px py pz qx qy qz qw scale");
+                recs.insert(recs.end(), v, v + 8);
+            }
+            files.push_back(e);
+        }
+    }
+    const size_t bytes = sizeof(vpt_ins_header) + files.size() * sizeof(vpt_ins_file_entry) + recs.size() * sizeof(double);
+    char* blk = (char*)malloc(bytes);
+    if (!blk) return fail(nullptr, VPT_ERR_IO, "vpt_ins_load: out of memory");
+    vpt_ins_header h; h.kind = kind; h.n_files = (int32_t)files.size(); h.n_records = (int32_t)(recs.size() / 8); h.reserved = 0;
+    memcpy(blk, &h, sizeof(h));
+    if (!files.empty()) memcpy(blk + sizeof(h), files.data(), files.size() * sizeof(vpt_ins_file_entry));
+    if (!recs.empty()) memcpy(blk + sizeof(h) + files.size() * sizeof(vpt_ins_file_entry), recs.data(), recs.size() * sizeof(double));
+    *out = reinterpret_cast<vpt_ins_header*>(blk);
+    return VPT_OK;
+}
 
 int vpt_vdb_load(const char* path, const char* grid_name, float** values_out, int info[13], float xform16[16], float stats[4]) {
     if (!path || !grid_name || !values_out) return fail(nullptr, VPT_ERR_INVALID, "vpt_vdb_load: null argument");

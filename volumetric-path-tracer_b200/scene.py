@@ -240,6 +240,42 @@ class Volume:
         return g
 
 
+def load_ins(path):
+    """Parse a reference `.ins` scene / light file (read_instance_file, main.cpp:980-1040) with the library's reader.
+    -> {"kind": "volumes", "files": [{"path": str, "instances": [(pos3, quat4, scale), ...]}, ...]}
+     | {"kind": "lights",  "lights": [(pos3, rgb3, power), ...]}"""
+    hp = C.POINTER(N.ins_header)()
+    check(lib.vpt_ins_load(os.fsencode(path), C.byref(hp)), None, "vpt_ins_load")
+    try:
+        h = hp.contents
+        base = C.addressof(h) + C.sizeof(N.ins_header)
+        entries = (N.ins_file_entry * h.n_files).from_address(base)
+        recs = np.ctypeslib.as_array((C.c_double * (8 * h.n_records)).from_address(base + h.n_files * C.sizeof(N.ins_file_entry))).reshape(-1, 8).copy()
+        if h.kind == 1:
+            return {"kind": "lights", "lights": [(tuple(r[0:3]), tuple(r[3:6]), float(r[6])) for r in recs]}
+        files = []
+        for e in entries:
+            rr = recs[e.first_record:e.first_record + e.n_instances]
+            files.append({"path": e.path.decode(), "instances": [(tuple(r[0:3]), tuple(r[3:7]), float(r[7])) for r in rr]})
+        return {"kind": "volumes", "files": files}
+    finally:
+        lib.vpt_free(hp)
+
+
+def scene_from_ins(path, env=None, resolve=None, device="cuda:0"):
+    """Build a Scene the way the reference does for an `.ins` argument (main.cpp:1040-1102): every listed .vdb is loaded once
+    and instanced with its (position, quaternion, scale) records; a "light" file yields the point-light list instead.
+    `resolve(path) -> path` maps the verbatim paths of the file (the reference uses them relative to its CWD)."""
+    d = load_ins(path)
+    if d["kind"] == "lights":
+        return d["lights"]
+    instances = []
+    for f in d["files"]:
+        vol = Volume.load_vdb(resolve(f["path"]) if resolve else f["path"])
+        instances += [vol.instance(pos, quat, scale) for pos, quat, scale in f["instances"]]
+    return Scene(instances, env=env, device=device)
+
+
 def synthetic_env(width=3000, height=1500):
     """Procedural HDR sky of the reference HDRI's shape, used only when the asset is not on the box."""
     v = np.linspace(0.0, 1.0, height, dtype=np.float32)[:, None]
