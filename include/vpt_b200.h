@@ -104,6 +104,11 @@ int  vpt_texture_create_env(const float* host_rgba, unsigned width, unsigned hei
  * version reads/writes one element outside its arrays at the row starts (cdf_p - 1, marginal_cdf_p - 1); this one
  * uses 0 for those out-of-range reads. */
 int  vpt_env_tables_create(const float* func, unsigned res, vpt_tex_t tex_out[4], void* arrays_out[4], float* marginal_int_out);
+/* The table create_cdf feeds into the above: luminous power of the reference's HOST-side analytic sky (single-scattering
+ * Rayleigh + Mie march, 16 x 8 samples, main.cpp:242-301) over res x res directions, func[y*res + x] =
+ * |sky(dir(az = x/(res-1)*2pi, el = y/(res-1)*pi)) * sky_color| (main.cpp:683-693; the reference uses res = 180 and
+ * Kernel_params.azimuth / elevation / sky_color).  Pure host code, no device needed. */
+int  vpt_env_sky_tabulate(float azimuth_deg, float elevation_deg, const float sky_color[3], unsigned res, float* func_out);
 int  vpt_texture_destroy(vpt_tex_t tex, void* array);
 
 /* Minimal OpenVDB (file format 224) reader: densify grid `grid_name` over its active-voxel bounding box

@@ -151,7 +151,7 @@ EXPORTED_SYMBOLS = [
     "vpt_texture_create_3d", "vpt_texture_create_env", "vpt_texture_destroy", "vpt_vdb_load", "vpt_hdr_load",
     "vpt_bmp_load_rbg", "vpt_exr_load_rgb", "vpt_free", "vpt_octree_build", "vpt_octree_destroy", "vpt_volume_bounds",
     "vpt_camera_look_at", "vpt_kernel_params_defaults", "vpt_get_counters", "vpt_get_kernel_times", "vpt_octree_read",
-    "vpt_env_tables_create", "vpt_ins_load",
+    "vpt_env_tables_create", "vpt_ins_load", "vpt_env_sky_tabulate",
 ]
 
 # ---- prototypes ------------------------------------------------------------------------------------
@@ -188,6 +188,7 @@ class ins_file_entry(C.Structure):
     _fields_ = [("path", C.c_char * 1024), ("first_record", C.c_int32), ("n_instances", C.c_int32)]
 
 
+lib.vpt_env_sky_tabulate.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_float), C.c_uint, C.POINTER(C.c_float)]; lib.vpt_env_sky_tabulate.restype = C.c_int
 lib.vpt_ins_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(ins_header))]; lib.vpt_ins_load.restype = C.c_int
 lib.vpt_vdb_load.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float)]
 lib.vpt_vdb_load.restype = C.c_int

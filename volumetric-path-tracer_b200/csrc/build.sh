@@ -13,6 +13,7 @@ $NVCC $ARCH -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-ffp-contract=off -c "$HER
 $NVCC $ARCH -O2 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off ${VPT_KERNEL_DEFS:-} -x cu -c "$HERE/host/vpt_context.cpp" -o "$HERE/_obj/vpt_context.o"
 g++ -O2 -std=c++17 -fPIC -c "$HERE/host/vdb_reader.cpp" -o "$HERE/_obj/vdb_reader.o"
 g++ -O2 -std=c++17 -fPIC -c "$HERE/host/image_io.cpp" -o "$HERE/_obj/image_io.o"
+g++ -O2 -std=c++17 -fPIC -ffp-contract=off -c "$HERE/host/sky_table.cpp" -o "$HERE/_obj/sky_table.o"
 LIBNAME="${VPT_LIB_NAME:-libvpt_b200.so}"
 $NVCC $ARCH -shared -o "$OUT/$LIBNAME" "$HERE"/_obj/*.o -lz
 echo "built $OUT/$LIBNAME"

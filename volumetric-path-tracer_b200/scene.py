@@ -66,6 +66,14 @@ def texture_env(rgba: np.ndarray) -> Texture:
     return Texture(tex.value, arr)
 
 
+def sky_power_table(azimuth=120.0, elevation=30.0, sky_color=(1.0, 1.0, 1.0), res=180) -> np.ndarray:
+    """The res x res table create_cdf builds from the reference's host-side analytic sky (vpt_env_sky_tabulate)."""
+    out = np.empty((res, res), dtype=np.float32)
+    col = (C.c_float * 3)(*[float(c) for c in sky_color])
+    check(lib.vpt_env_sky_tabulate(float(azimuth), float(elevation), col, int(res), out.ctypes.data_as(C.POINTER(C.c_float))), None, "vpt_env_sky_tabulate")
+    return out
+
+
 class EnvTables:
     """Sky-sampling tables of the volumetric path integrator (Kernel_params.env_*_tex), built by vpt_env_tables_create."""
     def __init__(self, func: np.ndarray):
