@@ -285,10 +285,10 @@ def test_volumetric_path_integrator_against_reference(dragon, cfg):
     dfrac = flipped_fraction(mine.buffers.depth.cpu().numpy()[:, None], ref.buffers.depth.cpu().numpy()[:, None])
     print(f"vol cfg {cfg}: ref mean {float(want.mean()):.6g} ours {float(got.mean()):.6g} flipped {frac:.3g} depth-flipped {dfrac:.3g}")
     assert np.isfinite(want).all() and float(want.mean()) > 1e-3
-    # HDRI configurations are bit-exact.  With the tabulated sky (env 0) the sky model is also evaluated INSIDE the path (at the
-    # scatter point, ~3 m above the model's 6.36e6 m planet radius), where it amplifies 1-ulp differences of its inputs to ~1 %:
-    # measured 99.75-99.85 % of pixels within tolerance, bounded here at 99.5 %.
-    limit = 5e-3 if cfg["env"] == 0 else 0.0
+    # Measured: no pixel outside tolerance in any configuration.  With the tabulated sky (env 0) the sky model is also evaluated
+    # INSIDE the path, where the reference build contracts three ill-conditioned sums differently from its end-of-path call sites;
+    # vpt_atmosphere.cuh mirrors both orders (kInPath).  Before that 0.25 % of the pixels were off by up to 1 %.
+    limit = 1e-4 if cfg["env"] == 0 else 0.0
     assert frac <= limit and dfrac == 0.0
     raw_m = mine.buffers.raw.cpu().numpy().reshape(-1, 4)[:, 3]; raw_r = ref.buffers.raw.cpu().numpy().reshape(-1, 4)[:, 3]
     assert np.mean(np.abs(raw_m - raw_r) > 1e-5) <= MAX_FLIPPED

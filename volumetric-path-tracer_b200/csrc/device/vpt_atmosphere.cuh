@@ -21,6 +21,12 @@ constexpr int kSkyTransW = 256, kSkyTransH = 64;
 constexpr int kSkyScatR = 32, kSkyScatMu = 128, kSkyScatMuS = 32, kSkyScatNu = 8;
 constexpr int kSkyIrrW = 256, kSkyIrrH = 64;
 
+// kInPath selects the operation order of the reference's IN-PATH call sites (estimate_sky, render_kernel.cu:1382 / :1429) instead of
+// its end-of-path ones (:1752 / :1840): ptxas contracted three ill-conditioned sums differently there (read off the SASS of both):
+//     c*c + (pdv*pdv - pdp)          tail: FMUL, FADD       in path: FFMA(c, c, .)
+//     (rmu*rmu - r*r) + Rt*Rt        tail: FADD + FMUL(Rt*Rt)   in path: FFMA(Rt, Rt, .)      (both radiance functions)
+// With r ~ 6.36e6 m a product rounded to fp32 is off by up to 2e6 m^2, so the two forms give visibly different look-up coordinates.
+template <bool kInPath>
 struct Sky {
     const vpt_atmosphere& a;
     float Rg, Rt;                      // bottom / top radius
@@ -147,7 +153,8 @@ struct Sky {
     VPT_DEV float3 sky_radiance(float3 cam, float3 view, float3 sun, float3& transmittance) const {
         float r = length(cam);
         float rmu = dot(cam, view);
-        const float to_top = -rmu - sqrt(rmu * rmu - r * r + Rt * Rt);
+        const float s2 = pfma(-r, r, pmul(rmu, rmu));                                   // rmu^2 - r^2
+        const float to_top = psub(-rmu, sqrtf(kInPath ? pfma(Rt, Rt, s2) : padd(s2, pmul(Rt, Rt))));
         if (to_top > 0.0f) {                     // viewer in space: move to the boundary
             cam = cam + view * to_top;
             r = Rt;
@@ -173,7 +180,8 @@ struct Sky {
         const float3 view = normalize(pt - cam);
         float r = length(cam);
         float rmu = dot(cam, view);
-        const float to_top = -rmu - sqrt(rmu * rmu - r * r + Rt * Rt);
+        const float s2 = pfma(rmu, rmu, -pmul(r, r));                                   // rmu^2 - r^2 (the product fused here is the other one)
+        const float to_top = psub(-rmu, sqrtf(kInPath ? pfma(Rt, Rt, s2) : padd(s2, pmul(Rt, Rt))));
         if (to_top > 0.0f) {
             cam = cam + view * to_top;
             r = Rt;
@@ -228,17 +236,18 @@ struct Sky {
 
 // Environment radiance of the precomputed sky for a ray leaving the scene (:839-886).  The scene sits on the
 // planet's surface: planet centre = (0, -bottom_radius, 0) in world units (metres).
+template <bool kInPath = false>
 VPT_DEV float3 sample_atmosphere(const vpt_atmosphere& atm, float azimuth, float elevation, float3 ray_pos, float3 ray_dir)
 {
-    const Sky sky(atm);
+    const Sky<kInPath> sky(atm);
     const float3 centre = f3(.0f, -atm.bottom_radius, .0f);
     const float3 sun = sun_direction(azimuth, elevation);
 
     const float3 p = ray_pos - centre;
     const float p_dot_v = dot(p, ray_dir);
     const float p_dot_p = dot(p, p);
-    const float dist2 = p_dot_p - p_dot_v * p_dot_v;
-    const float to_ground = -p_dot_v - sqrt(centre.y * centre.y - dist2);
+    const float q = psub(pmul(p_dot_v, p_dot_v), p_dot_p);                              // -(squared distance of the line from the centre)
+    const float to_ground = psub(-p_dot_v, sqrtf(kInPath ? pfma(centre.y, centre.y, q) : padd(pmul(centre.y, centre.y), q)));
 
     float ground_alpha = 0.0f;
     float3 ground = f3(0.0f);

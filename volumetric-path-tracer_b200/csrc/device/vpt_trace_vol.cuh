@@ -33,7 +33,7 @@ VPT_DEV float3 env_tex_radiance(const vpt_kernel_params& kp, float3 wi) {
 
 // one out-of-line copy of the sky model for the in-kernel uses (three call sites, ~2000 instructions each otherwise)
 __device__ __noinline__ float3 sky_radiance_noinline(const vpt_atmosphere& atm, float az, float el, float3 pos, float3 wi) {
-    return sample_atmosphere(atm, az, el, pos, wi);
+    return sample_atmosphere<true>(atm, az, el, pos, wi);        // the reference's in-path operation order (vpt_atmosphere.cuh)
 }
 
 // direction from the tabulated sky distribution (reference draw_sample_from_distribution, :167-246); `peek` is a COPY of the
