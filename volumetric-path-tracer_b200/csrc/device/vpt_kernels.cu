@@ -1,19 +1,19 @@
 // vpt_kernels.cu -- sm_100a wavefront kernels that replace the reference megakernel
-// `volume_rt_kernel` (source/render_kernel.cu:2216-2326) for the direct integrator.
+// `volume_rt_kernel` (source/render_kernel.cu:2216-2326), both integrators.
 //
 //   k_prepare_scene : GPU_VDB[] + OCTNode tree (the reference launch parameters) -> flat scene tables
-//   k_generate      : one thread per (pixel, pass): Philox stream, blue-noise jitter, thin-lens ray,
-//                     root/sphere test; misses write their sample record, hits are pushed into a
-//                     warp-compacted ray queue (one atomic per warp, 32-byte records)
-//   k_trace         : persistent threads; every lane owns one ray and runs ONE unified tracking
-//                     step body (delta / residual-ratio / emission walks); estimator transitions are
-//                     batched so the step loop stays converged; finished lanes refill from the queue
-//   k_resolve       : per pixel, passes in order: environment term, NaN guard, running mean, ACES
-//                     tonemap, display/raw/depth/cost writes (the tail of the reference kernel)
-//   k_bn_advance    : golden-ratio advance of the 256x256 blue-noise buffer (race-free, quirk Q6)
+//   k_bn_prepare    : per-chunk blue-noise jitter table + golden-ratio advance of the 256x256 buffer (race-free, quirk Q6)
+//   k_generate      : one block per 32x4 pixel tile, all passes of the chunk: Philox stream, jitter, thin-lens ray,
+//                     root/sphere test, draw-free prefix of the first tracking walk; misses write a 16-byte sample
+//                     record, the rest are pushed into a warp-compacted ray queue (one atomic per warp)
+//   k_trace<I, L>   : persistent; every lane owns three rays parked in shared memory (vpt_trace.cuh); I = integrator
+//                     (0 direct, 1 volumetric path: vpt_trace_vol.cuh), L = lean instantiation for the common scene
+//   k_resolve<S>    : per pixel, passes in order: environment term (S = 0 HDRI, 1 / 2 precomputed sky: vpt_atmosphere.cuh),
+//                     NaN guard, running mean, ACES tonemap, display/raw/depth/cost writes (the tail of the reference kernel)
+//   k_bn_advance, k_unpermute : blue-noise advance for non-sampling passes; stripe un-permutation after the multi-GPU gather
 //
-// Numerics: compiled with the reference's flags (--use_fast_math); decision-relevant expressions keep
-// the reference's operand order so a pixel's path is reproduced sample for sample (see vpt_math.cuh).
+// Numerics: compiled with the reference's flags (--use_fast_math); decision-relevant expressions keep the reference
+// build's operation order (read off its SASS) so a pixel's path is reproduced sample for sample (see vpt_math.cuh).
 #include <type_traits>
 #include "vpt_walk.cuh"
 #include "vpt_atmosphere.cuh"

@@ -4,8 +4,8 @@
 // Scheduling of one vpt_render_passes(n) call on the caller's stream (no host synchronisation):
 //   [once per (volumes, octree) pair]  k_prepare_scene
 //   for each chunk of <= passes_per_chunk sampled passes:
-//        memset(queue counters) -> k_generate -> k_trace (persistent) -> k_resolve
-//   k_bn_advance(n)
+//        memset(queue counters) -> k_bn_prepare -> k_generate -> k_trace<integrator, lean> (persistent) -> k_resolve<env>
+//   passes beyond max_interactions / render == false: k_resolve (re-tonemap) + k_bn_advance
 // which leaves every buffer named by Kernel_params in the state n reference launches would.
 #include "../../../include/vpt_b200.h"
 #include "../device/vpt_kernels.h"
