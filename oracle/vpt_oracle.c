@@ -54,6 +54,16 @@ static void philox(uint32_t c0, uint32_t c1, uint32_t key, uint32_t out[4]) {
     }
     out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
 }
+/* test hooks: one Philox block, and draw k of the stream curand_init(idx, 0, iteration*4096) yields */
+void orc_philox_block(uint32_t c0, uint32_t c1, uint32_t key, uint32_t out[4]) { philox(c0, c1, key, out); }
+static void rng_init(rng_t* r, uint32_t idx, uint32_t iteration);
+static float rnd(rng_t* r);
+float orc_stream_draw(uint32_t idx, uint32_t iteration, uint32_t k) {
+    rng_t r; rng_init(&r, idx, iteration);
+    float v = 0.f;
+    for (uint32_t i = 0; i <= k; ++i) v = rnd(&r);
+    return v;
+}
 static void rng_init(rng_t* r, uint32_t idx, uint32_t iteration) { r->key = idx; r->base = (iteration * 4096u) >> 2; r->k = 0; r->cached = 0xffffffffu; }
 static float rnd(rng_t* r) {
     uint32_t b = r->k >> 2;

@@ -47,3 +47,43 @@ def test_cpu_port_is_deterministic_and_progressive():
     orc.reset_blue_noise()
     _, a2, _, _ = run_case("dragon_single")
     assert np.array_equal(a1, a2)
+
+
+def _philox4x32_10(ctr, key):
+    """Generic Philox4x32-10 (Salmon et al., SC'11; Random123) in Python integers."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    x0, x1, x2, x3 = ctr; k0, k1 = key
+    for _ in range(10):
+        p0, p1 = M0 * x0, M1 * x2
+        x0, x1, x2, x3 = ((p1 >> 32) ^ x1 ^ k0) & 0xffffffff, p1 & 0xffffffff, ((p0 >> 32) ^ x3 ^ k1) & 0xffffffff, p0 & 0xffffffff
+        k0 = (k0 + W0) & 0xffffffff; k1 = (k1 + W1) & 0xffffffff
+    return (x0, x1, x2, x3)
+
+
+def test_philox_known_answers_and_curand_stream_addressing():
+    """Pins the generator of the path: Random123's published known-answer vectors for philox4x32-10, then the
+    oracle's block function and its (pixel, iteration, draw) addressing = curand_init(idx, 0, iteration*4096) + curand_uniform."""
+    import ctypes as C
+    import oracle_cpu
+    # Random123 kat_vectors: philox4x32 10
+    assert _philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert _philox4x32_10((0xffffffff,) * 4, (0xffffffff,) * 2) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert _philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+    lib = C.CDLL(oracle_cpu.LIB)
+    lib.orc_philox_block.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]; lib.orc_philox_block.restype = None
+    lib.orc_stream_draw.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]; lib.orc_stream_draw.restype = C.c_float
+    rs = np.random.RandomState(7)
+    for c0, c1, key in [(0, 0, 0), (1, 0, 12345), (0xffffffff, 1, 0xdeadbeef)] + [tuple(int(v) for v in rs.randint(0, 2**32, 3, dtype=np.uint64)) for _ in range(20)]:
+        out = (C.c_uint32 * 4)()
+        lib.orc_philox_block(c0, c1, key, out)
+        assert tuple(out) == _philox4x32_10((c0, c1, 0, 0), (key, 0))
+    # stream addressing: seed = pixel index (key word 0), subsequence 0, offset = iteration*4096 draws => counter = offset/4 + k/4,
+    # lane k%4, with the carry into counter word 1; uniform = x * 2^-32 + 2^-33 (curand_uniform.h:69-72)
+    for idx, it, k in [(0, 0, 0), (5, 0, 3), (123456, 7, 9), (2073599, 63, 41), (77, 4194303, 2), (77, 4194304, 5)]:
+        off = (it * 4096) & 0xffffffff                         # the reference passes an unsigned int product
+        blk = ((off >> 2) + (k >> 2))
+        c0, c1 = blk & 0xffffffff, blk >> 32
+        x = _philox4x32_10((c0, c1, 0, 0), (idx, 0))[k & 3]
+        want = np.float32(np.float32(x) * np.float32(2.3283064e-10) + np.float32(2.3283064e-10 / 2))
+        got = lib.orc_stream_draw(idx, it, k)
+        assert abs(float(got) - float(want)) <= 1.2e-7 * max(1.0, float(want)), (idx, it, k, got, want)
