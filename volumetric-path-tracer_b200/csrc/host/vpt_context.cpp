@@ -441,11 +441,16 @@ int vpt_env_tables_create(const float* func, unsigned res, vpt_tex_t tex_out[4],
     const float marginal_int = run;
     if (marginal_int > 0.f) for (unsigned y = 0; y < res; ++y) mcdf[y] /= std::max(.000001f, marginal_int);
     *marginal_int_out = marginal_int;
-    int rc;
-    if ((rc = create_table_texture(func, res, res, &tex_out[0], &arrays_out[0])) != VPT_OK) return rc;
-    if ((rc = create_table_texture(cdf.data(), res, res, &tex_out[1], &arrays_out[1])) != VPT_OK) return rc;
-    if ((rc = create_table_texture(mfunc.data(), res, 0, &tex_out[2], &arrays_out[2])) != VPT_OK) return rc;
-    if ((rc = create_table_texture(mcdf.data(), res, 0, &tex_out[3], &arrays_out[3])) != VPT_OK) return rc;
+    const float* src[4] = { func, cdf.data(), mfunc.data(), mcdf.data() };
+    const unsigned heights[4] = { res, res, 0u, 0u };
+    for (int i = 0; i < 4; ++i) { tex_out[i] = 0; arrays_out[i] = nullptr; }
+    for (int i = 0; i < 4; ++i) {
+        const int rc = create_table_texture(src[i], res, heights[i], &tex_out[i], &arrays_out[i]);
+        if (rc != VPT_OK) {                                       // leave nothing half-built behind
+            for (int j = 0; j < i; ++j) { vpt_texture_destroy(tex_out[j], arrays_out[j]); tex_out[j] = 0; arrays_out[j] = nullptr; }
+            return rc;
+        }
+    }
     return VPT_OK;
 }
 
