@@ -72,8 +72,10 @@ int  vpt_unpermute(vpt_context* ctx, const void* d_gathered, void* d_full, unsig
 int  vpt_render_pass(vpt_context* ctx, void* const params[VPT_NUM_ARGS], void* stream);
 int  vpt_render_passes(vpt_context* ctx, void* const params[VPT_NUM_ARGS], unsigned n_passes, void* stream);
 
-/* The flattened scene tables are cached per (volumes pointer, octree root pointer); call this after the
- * application rebuilt either in place. */
+/* The flattened scene tables are cached per (volumes pointer, octree root pointer, build generation of a vpt_octree_build
+ * octree) and refreshed whenever a call arrives with Kernel_params.iteration == 0 (the reference application resets the
+ * iteration on every scene edit, main.cpp:1667-1780).  Call this only if the GPU_VDB[] array or a foreign octree was
+ * rewritten in place WITHOUT restarting the accumulation. */
 int  vpt_invalidate_scene(vpt_context* ctx);
 
 /* Counters of the last vpt_render_pass(es) call: kernels launched, and (after the stream has been
@@ -135,15 +137,45 @@ typedef struct vpt_ins_header { int32_t kind; int32_t n_files; int32_t n_records
 typedef struct vpt_ins_file_entry { char path[1024]; int32_t first_record; int32_t n_instances; } vpt_ins_file_entry;
 int  vpt_ins_load(const char* path, vpt_ins_header** out);
 
-/* Depth-3 octree over instance bounds in the reference's own node layout (bvh_builder.cpp:61-96 +
- * bvh_kernels.cu:204-246), built in parallel (one thread per node, no device heap, no 600-volume
- * overflow: n > VPT_OCT_MAX_VOLUMES is rejected).  h_volumes: host array of n GPU_VDB.
- * *d_root_out: device pointer to node 0 of a contiguous 585-node array (free with vpt_octree_destroy). */
+/* Instance acceleration build -- replaces BVH_Builder::build_bvh (bvh_builder.cpp:46-105).
+ *
+ * vpt_octree_build: depth-3 octree over the instance bounds (host root set-up bvh_builder.cpp:61-78, node semantics of
+ * bvh_kernels.cu:204-246: child boxes by halving, inclusive overlap test, ascending instance order), built in parallel
+ * with no device heap.  Any n >= 1:
+ *   n <= VPT_OCT_MAX_VOLUMES  *d_root_out is node 0 of a contiguous 585-node tree in the reference's own OCTNode layout
+ *                             (pointer-linked; the reference kernel can consume it as well);
+ *   n >  VPT_OCT_MAX_VOLUMES  the reference layout cannot hold the lists (vol_indices[600]; the reference itself overflows
+ *                             the node there, quirk Q11): *d_root_out points to the root record only (children null).
+ * In both cases the octree is ALSO kept in the flat form the render kernels read (73 internal nodes + 512 leaf lists in
+ * CSR form, no per-leaf limit) and registered under the returned root pointer: vpt_render_pass(es) recognises the pointer
+ * in params[VPT_ARG_OCTREE] and uses those tables directly.  h_volumes: host array of n GPU_VDB; the GPU_VDB[] device
+ * array passed at render time must describe the same instances.  Free with vpt_octree_destroy. */
 int  vpt_octree_build(const vpt_gpu_vdb* h_volumes, int n, vpt_devptr_t* d_root_out);
 int  vpt_octree_destroy(vpt_devptr_t d_root);
-/* Copy any pointer-linked octree (this builder's or the reference's device-heap one) into 585 host nodes in the
- * canonical numbering 0 | 1+c1 | 9+c1*8+c2 | 73+c1*64+c2*8+c3; exists[j] = 0 for nodes never allocated. */
+/* What vpt_octree_build registered for this root: instance count, whether reference-layout nodes exist (n <= 600), total
+ * and largest leaf-list length.  Any output pointer may be NULL. */
+int  vpt_octree_info(vpt_devptr_t d_root, int* n_instances, int* reference_layout, long long* total_leaf_entries, int* max_leaf_entries);
+/* Copy any pointer-linked octree (this builder's n <= 600 tree or the reference's device-heap one) into 585 host nodes in
+ * the canonical numbering 0 | 1+c1 | 9+c1*8+c2 | 73+c1*64+c2*8+c3; exists[j] = 0 for nodes never allocated. */
 int  vpt_octree_read(vpt_devptr_t d_root, vpt_octnode* h_nodes585, int* h_exists585);
+/* Flat leaf lists of a registered octree: leaf_offset_count[2*l] / [2*l+1] = offset / length of leaf l = c1*64+c2*8+c3 in
+ * `indices` (ascending instance ids; capacity in ints, indices may be NULL to fetch the table only). */
+int  vpt_octree_read_flat(vpt_devptr_t d_root, unsigned leaf_offset_count[1024], int* indices, long long capacity);
+
+/* LBVH over the instance AABBs in the reference's BVHNode layout (BuildBVH, bvh_kernels.cu:460-580: Morton codes of the
+ * centroids in the scene box, stable sort, Karras radix tree with the (code, id) tie-break, bottom-up refit).
+ * *d_nodes_out: n-1 internal nodes (node 0 is the root; one zeroed node when n == 1), *d_leaves_out: n leaves in sorted
+ * order; child / parent fields are device pointers into the two arrays, exactly what the reference passes as `root_node`.
+ * scene_bounds6 (may be NULL): union of the instance boxes.  h_sorted_codes / h_sorted_ids (host, n entries, may be NULL):
+ * the sorted 30-bit Morton codes and instance ids.  Unlike the reference the arrays are zero-initialised and n == 1 is
+ * handled (quirk Q18).  The live integrators of the reference never traverse this tree; it is built for
+ * callers that pass it on. */
+int  vpt_bvh_build(const vpt_gpu_vdb* h_volumes, int n, vpt_devptr_t* d_nodes_out, vpt_devptr_t* d_leaves_out, float scene_bounds6[6],
+                   unsigned long long* h_sorted_codes, int* h_sorted_ids);
+/* Copy a BVH in that layout (either builder's) to the host, pointer fields rewritten as indices: internal node i -> i,
+ * leaf i -> (n-1)+i, anything else -> (uint64)-1. */
+int  vpt_bvh_read(vpt_devptr_t d_nodes, vpt_devptr_t d_leaves, int n, vpt_bvhnode* h_nodes, vpt_bvhnode* h_leaves);
+int  vpt_bvh_destroy(vpt_devptr_t d_nodes, vpt_devptr_t d_leaves);
 /* AABB of one instance (GPU_VDB::Bounds, gpu_vdb.h:131-146): out6 = pmin, pmax. */
 void vpt_volume_bounds(const vpt_gpu_vdb* h_volume, float out6[6]);
 

@@ -177,3 +177,56 @@ def test_env_sky_tabulation_matches_independent_restatement(az, el):
     # colour scaling is linear (intensity multiplies the radiance, main.cpp:300)
     half = sky_power_table(az, el, (0.5, 0.5, 0.5), res).astype(np.float64)
     assert np.allclose(half, 0.5 * got, rtol=1e-5)
+
+
+def _mutations(blob, seed, n, header_bias=400):
+    """Deterministic single-field corruptions: truncations, 1/4/8-byte overwrites with extreme values, mostly in the header
+    region where the offsets / counts / sizes live."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for i in range(n):
+        b = bytearray(blob)
+        kind = i % 4
+        if kind == 0:
+            out.append(bytes(b[:int(rng.randint(1, len(b)))])); continue
+        pos = int(rng.randint(0, min(len(b) - 8, header_bias))) if rng.rand() < 0.7 else int(rng.randint(0, len(b) - 8))
+        pick = lambda vals: vals[int(rng.randint(0, len(vals)))]
+        if kind == 1: b[pos] = pick([0, 1, 0x7f, 0x80, 0xff])
+        elif kind == 2: b[pos:pos + 4] = pick([0, 0x7fffffff, 0x80000000, 0xffffffff, 0xfffffff0]).to_bytes(4, "little")
+        else: b[pos:pos + 8] = pick([0, 0x7fffffffffffffff, 0x8000000000000000, 0xffffffffffffffff, len(b) + 1, 0xfffffffffffffff0]).to_bytes(8, "little")
+        out.append(bytes(b))
+    return out
+
+
+def test_corrupt_vdb_files_fail_cleanly(tmp_path):
+    """sizes and offsets taken from the file (grid/block/end positions, Blosc block starts, typesize, bbox) must be
+    validated: a malformed .vdb either decodes or raises VptError -- it never reads out of bounds (this test would crash)."""
+    blob = open(find_asset("dragon.vdb"), "rb").read()
+    # the descriptor offsets live right after the grid name/type strings: make sure those bytes are hit, too
+    at = blob.index(b"Tree_float_5_4_3")
+    p = tmp_path / "m.vdb"
+    ok = bad = 0
+    for m in _mutations(blob, 5, 160) + _mutations(blob[:at + 200] + blob[at + 200:], 6, 80, header_bias=at + 120):
+        p.write_bytes(m)
+        try:
+            got = load_vdb_grid(str(p), "density")
+            ok += 1
+            if got is not None: assert got[0].size <= 1 << 28
+        except V.VptError:
+            bad += 1
+    assert bad > 40 and ok + bad == 240
+
+
+def test_corrupt_image_files_fail_cleanly(tmp_path):
+    for name, loader in (("blackbody_texture.exr", load_exr_rgb), ("BN0.bmp", load_bmp_rbg)):
+        blob = open(find_asset(name), "rb").read()
+        p = tmp_path / ("m" + os.path.splitext(name)[1])
+        bad = 0
+        for m in _mutations(blob, 9, 200, header_bias=min(len(blob) - 8, 700)):
+            p.write_bytes(m)
+            try:
+                img = loader(str(p))
+                assert img.size <= 1 << 28
+            except V.VptError:
+                bad += 1
+        assert bad > 20, name

@@ -22,5 +22,6 @@ if rank == 0:
     one.render(P); torch.cuda.synchronize()
     ok = torch.equal(full.view(-1, 3), one.buffers.accum)
     print(f"[mgpu_check] world={world} gathered == single-GPU frame: {ok}; mean {float(full.mean()):.6f}", flush=True)
+    if ok: print("BITWISE_OK", flush=True)
 dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -152,6 +152,7 @@ EXPORTED_SYMBOLS = [
     "vpt_bmp_load_rbg", "vpt_exr_load_rgb", "vpt_free", "vpt_octree_build", "vpt_octree_destroy", "vpt_volume_bounds",
     "vpt_camera_look_at", "vpt_kernel_params_defaults", "vpt_get_counters", "vpt_get_kernel_times", "vpt_octree_read",
     "vpt_env_tables_create", "vpt_ins_load", "vpt_env_sky_tabulate",
+    "vpt_octree_info", "vpt_octree_read_flat", "vpt_bvh_build", "vpt_bvh_read", "vpt_bvh_destroy",
 ]
 
 # ---- prototypes ------------------------------------------------------------------------------------
@@ -199,6 +200,12 @@ lib.vpt_free.argtypes = [_vp]; lib.vpt_free.restype = None
 lib.vpt_octree_build.argtypes = [C.POINTER(GPU_VDB), C.c_int, C.POINTER(C.c_uint64)]; lib.vpt_octree_build.restype = C.c_int
 lib.vpt_octree_destroy.argtypes = [C.c_uint64]; lib.vpt_octree_destroy.restype = C.c_int
 lib.vpt_octree_read.argtypes = [C.c_uint64, C.POINTER(OCTNode), C.POINTER(C.c_int)]; lib.vpt_octree_read.restype = C.c_int
+lib.vpt_octree_info.argtypes = [C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]; lib.vpt_octree_info.restype = C.c_int
+lib.vpt_octree_read_flat.argtypes = [C.c_uint64, C.POINTER(C.c_uint), C.POINTER(C.c_int), C.c_longlong]; lib.vpt_octree_read_flat.restype = C.c_int
+lib.vpt_bvh_build.argtypes = [C.POINTER(GPU_VDB), C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_ulonglong), C.POINTER(C.c_int)]
+lib.vpt_bvh_build.restype = C.c_int
+lib.vpt_bvh_read.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.POINTER(BVHNode), C.POINTER(BVHNode)]; lib.vpt_bvh_read.restype = C.c_int
+lib.vpt_bvh_destroy.argtypes = [C.c_uint64, C.c_uint64]; lib.vpt_bvh_destroy.restype = C.c_int
 lib.vpt_volume_bounds.argtypes = [C.POINTER(GPU_VDB), C.POINTER(C.c_float)]; lib.vpt_volume_bounds.restype = None
 lib.vpt_camera_look_at.argtypes = [C.POINTER(camera), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float]
 lib.vpt_camera_look_at.restype = None

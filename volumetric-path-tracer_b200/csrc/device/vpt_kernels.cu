@@ -15,6 +15,7 @@
 // Numerics: compiled with the reference's flags (--use_fast_math); decision-relevant expressions keep the reference
 // build's operation order (read off its SASS) so a pixel's path is reproduced sample for sample (see vpt_math.cuh).
 #include <type_traits>
+#include <cstring>
 #include "vpt_walk.cuh"
 #include "vpt_atmosphere.cuh"
 #include "vpt_kernels.h"
@@ -28,15 +29,59 @@ constexpr uint32_t kMissSentinel = 0xffffffffu;   // planeA.w bit pattern markin
 // =====================================================================================================
 __device__ __forceinline__ const vpt_octnode* oct_ptr(vpt_devptr_t p) { return reinterpret_cast<const vpt_octnode*>(p); }
 
+// per-volume world->index affine, evaluated with the reference's own adjugate formula order
+__device__ VolumeRec make_volume_rec(const vpt_gpu_vdb& g)
+{
+    // n_rc of the transposed matrix == xform[r-1][c-1] in memory order
+    const float n11 = g.xform[0][0], n12 = g.xform[0][1], n13 = g.xform[0][2], n14 = g.xform[0][3];
+    const float n21 = g.xform[1][0], n22 = g.xform[1][1], n23 = g.xform[1][2], n24 = g.xform[1][3];
+    const float n31 = g.xform[2][0], n32 = g.xform[2][1], n33 = g.xform[2][2], n34 = g.xform[2][3];
+    const float n41 = g.xform[3][0], n42 = g.xform[3][1], n43 = g.xform[3][2], n44 = g.xform[3][3];
+
+    const float t11 = n23 * n34 * n42 - n24 * n33 * n42 + n24 * n32 * n43 - n22 * n34 * n43 - n23 * n32 * n44 + n22 * n33 * n44;
+    const float t12 = n14 * n33 * n42 - n13 * n34 * n42 - n14 * n32 * n43 + n12 * n34 * n43 + n13 * n32 * n44 - n12 * n33 * n44;
+    const float t13 = n13 * n24 * n42 - n14 * n23 * n42 + n14 * n22 * n43 - n12 * n24 * n43 - n13 * n22 * n44 + n12 * n23 * n44;
+    const float t14 = n14 * n23 * n32 - n13 * n24 * n32 - n14 * n22 * n33 + n12 * n24 * n33 + n13 * n22 * n34 - n12 * n23 * n34;
+
+    const float det = n11 * t11 + n21 * t12 + n31 * t13 + n41 * t14;
+    const float idet = 1.0f / det;
+
+    // second and third output rows of the inverse (unscaled adjugate entries)
+    const float a01 = n24 * n33 * n41 - n23 * n34 * n41 - n24 * n31 * n43 + n21 * n34 * n43 + n23 * n31 * n44 - n21 * n33 * n44;
+    const float a11 = n13 * n34 * n41 - n14 * n33 * n41 + n14 * n31 * n43 - n11 * n34 * n43 - n13 * n31 * n44 + n11 * n33 * n44;
+    const float a21 = n14 * n23 * n41 - n13 * n24 * n41 - n14 * n21 * n43 + n11 * n24 * n43 + n13 * n21 * n44 - n11 * n23 * n44;
+    const float a31 = n13 * n24 * n31 - n14 * n23 * n31 + n14 * n21 * n33 - n11 * n24 * n33 - n13 * n21 * n34 + n11 * n23 * n34;
+
+    const float a02 = n22 * n34 * n41 - n24 * n32 * n41 + n24 * n31 * n42 - n21 * n34 * n42 - n22 * n31 * n44 + n21 * n32 * n44;
+    const float a12 = n14 * n32 * n41 - n12 * n34 * n41 - n14 * n31 * n42 + n11 * n34 * n42 + n12 * n31 * n44 - n11 * n32 * n44;
+    const float a22 = n12 * n24 * n41 - n14 * n22 * n41 + n14 * n21 * n42 - n11 * n24 * n42 - n12 * n21 * n44 + n11 * n22 * n44;
+    const float a32 = n14 * n22 * n31 - n12 * n24 * n31 - n14 * n21 * n32 + n11 * n24 * n32 + n12 * n21 * n34 - n11 * n22 * n34;
+
+    VolumeRec r;
+    r.m[0][0] = t11 * idet; r.m[0][1] = t12 * idet; r.m[0][2] = t13 * idet; r.adj3[0] = t14;
+    r.m[1][0] = a01 * idet; r.m[1][1] = a11 * idet; r.m[1][2] = a21 * idet; r.adj3[1] = a31;
+    r.m[2][0] = a02 * idet; r.m[2][1] = a12 * idet; r.m[2][2] = a22 * idet; r.adj3[2] = a32;
+    r.idet = idet;
+    r.bmin[0] = g.vdb_info.bmin.x; r.bmin[1] = g.vdb_info.bmin.y; r.bmin[2] = g.vdb_info.bmin.z;
+    r.rdim[0] = 1.0f / float(g.vdb_info.dim.x); r.rdim[1] = 1.0f / float(g.vdb_info.dim.y); r.rdim[2] = 1.0f / float(g.vdb_info.dim.z);
+    r.flags = (g.vdb_info.has_color ? 1u : 0u) | (g.vdb_info.has_emission ? 2u : 0u);
+    r.density_tex = g.vdb_info.density_texture; r.emission_tex = g.vdb_info.emission_texture; r.color_tex = g.vdb_info.color_texture;
+    return r;
+}
+
+// root == nullptr: the octree was built by vpt_octree_build, its flat tables already exist (`hdr` names them, any number of
+// instances) and only the per-volume records -- which depend on the GPU_VDB[] array handed in at render time -- are made here.
+// One kernel for both cases on purpose: the record arithmetic is then the very same machine code.
 __global__ void k_prepare_scene(const vpt_gpu_vdb* __restrict__ vols, const vpt_octnode* __restrict__ root,
                                 SceneTables* out, OctInternal* internal, uint2* leaf_list, int* leaf_indices,
-                                VolumeRec* vrec, int max_volumes)
+                                VolumeRec* vrec, int max_volumes, const SceneTables hdr)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
-    const int N = root->num_volumes;
+    const int N = root ? root->num_volumes : hdr.num_volumes;
+    if (!root && tid == 0) { SceneTables t = hdr; t.volumes = vrec; *out = t; }
 
-    if (tid == 0) {
+    if (root && tid == 0) {
         out->root_pmin[0] = root->bbox.pmin.x; out->root_pmin[1] = root->bbox.pmin.y; out->root_pmin[2] = root->bbox.pmin.z;
         out->root_pmax[0] = root->bbox.pmax.x; out->root_pmax[1] = root->bbox.pmax.y; out->root_pmax[2] = root->bbox.pmax.z;
         out->max_extinction = root->max_extinction;
@@ -47,7 +92,7 @@ __global__ void k_prepare_scene(const vpt_gpu_vdb* __restrict__ vols, const vpt_
     }
 
     // internal nodes: 0 = root, 1..8 = level 1, 9..72 = level 2
-    for (int j = tid; j < kOctInternalNodes; j += nthreads) {
+    for (int j = tid; root && j < kOctInternalNodes; j += nthreads) {
         const vpt_octnode* n = root;
         bool exists = true;
         if (j >= 1 && j < 9) { n = oct_ptr(root->children[j - 1]); }
@@ -72,7 +117,7 @@ __global__ void k_prepare_scene(const vpt_gpu_vdb* __restrict__ vols, const vpt_
     }
 
     // leaves: volume lists (instanced scenes); stride VPT_OCT_MAX_VOLUMES per leaf
-    for (int l = tid; l < kOctLeaves; l += nthreads) {
+    for (int l = tid; root && l < kOctLeaves; l += nthreads) {
         const int c1 = l >> 6, c2 = (l >> 3) & 7, c3 = l & 7;
         uint2 lst = make_uint2((uint32_t)l * VPT_OCT_MAX_VOLUMES, 0u);
         const vpt_octnode* p1 = oct_ptr(root->children[c1]);
@@ -88,45 +133,8 @@ __global__ void k_prepare_scene(const vpt_gpu_vdb* __restrict__ vols, const vpt_
         leaf_list[l] = lst;
     }
 
-    // per-volume world->index affine, evaluated with the reference's own adjugate formula order
-    for (int v = tid; v < N && v < max_volumes; v += nthreads) {
-        const vpt_gpu_vdb& g = vols[v];
-        // n_rc of the transposed matrix == xform[r-1][c-1] in memory order
-        const float n11 = g.xform[0][0], n12 = g.xform[0][1], n13 = g.xform[0][2], n14 = g.xform[0][3];
-        const float n21 = g.xform[1][0], n22 = g.xform[1][1], n23 = g.xform[1][2], n24 = g.xform[1][3];
-        const float n31 = g.xform[2][0], n32 = g.xform[2][1], n33 = g.xform[2][2], n34 = g.xform[2][3];
-        const float n41 = g.xform[3][0], n42 = g.xform[3][1], n43 = g.xform[3][2], n44 = g.xform[3][3];
-
-        const float t11 = n23 * n34 * n42 - n24 * n33 * n42 + n24 * n32 * n43 - n22 * n34 * n43 - n23 * n32 * n44 + n22 * n33 * n44;
-        const float t12 = n14 * n33 * n42 - n13 * n34 * n42 - n14 * n32 * n43 + n12 * n34 * n43 + n13 * n32 * n44 - n12 * n33 * n44;
-        const float t13 = n13 * n24 * n42 - n14 * n23 * n42 + n14 * n22 * n43 - n12 * n24 * n43 - n13 * n22 * n44 + n12 * n23 * n44;
-        const float t14 = n14 * n23 * n32 - n13 * n24 * n32 - n14 * n22 * n33 + n12 * n24 * n33 + n13 * n22 * n34 - n12 * n23 * n34;
-
-        const float det = n11 * t11 + n21 * t12 + n31 * t13 + n41 * t14;
-        const float idet = 1.0f / det;
-
-        // second and third output rows of the inverse (unscaled adjugate entries)
-        const float a01 = n24 * n33 * n41 - n23 * n34 * n41 - n24 * n31 * n43 + n21 * n34 * n43 + n23 * n31 * n44 - n21 * n33 * n44;
-        const float a11 = n13 * n34 * n41 - n14 * n33 * n41 + n14 * n31 * n43 - n11 * n34 * n43 - n13 * n31 * n44 + n11 * n33 * n44;
-        const float a21 = n14 * n23 * n41 - n13 * n24 * n41 - n14 * n21 * n43 + n11 * n24 * n43 + n13 * n21 * n44 - n11 * n23 * n44;
-        const float a31 = n13 * n24 * n31 - n14 * n23 * n31 + n14 * n21 * n33 - n11 * n24 * n33 - n13 * n21 * n34 + n11 * n23 * n34;
-
-        const float a02 = n22 * n34 * n41 - n24 * n32 * n41 + n24 * n31 * n42 - n21 * n34 * n42 - n22 * n31 * n44 + n21 * n32 * n44;
-        const float a12 = n14 * n32 * n41 - n12 * n34 * n41 - n14 * n31 * n42 + n11 * n34 * n42 + n12 * n31 * n44 - n11 * n32 * n44;
-        const float a22 = n12 * n24 * n41 - n14 * n22 * n41 + n14 * n21 * n42 - n11 * n24 * n42 - n12 * n21 * n44 + n11 * n22 * n44;
-        const float a32 = n14 * n22 * n31 - n12 * n24 * n31 - n14 * n21 * n32 + n11 * n24 * n32 + n12 * n21 * n34 - n11 * n22 * n34;
-
-        VolumeRec r;
-        r.m[0][0] = t11 * idet; r.m[0][1] = t12 * idet; r.m[0][2] = t13 * idet; r.adj3[0] = t14;
-        r.m[1][0] = a01 * idet; r.m[1][1] = a11 * idet; r.m[1][2] = a21 * idet; r.adj3[1] = a31;
-        r.m[2][0] = a02 * idet; r.m[2][1] = a12 * idet; r.m[2][2] = a22 * idet; r.adj3[2] = a32;
-        r.idet = idet;
-        r.bmin[0] = g.vdb_info.bmin.x; r.bmin[1] = g.vdb_info.bmin.y; r.bmin[2] = g.vdb_info.bmin.z;
-        r.rdim[0] = 1.0f / float(g.vdb_info.dim.x); r.rdim[1] = 1.0f / float(g.vdb_info.dim.y); r.rdim[2] = 1.0f / float(g.vdb_info.dim.z);
-        r.flags = (g.vdb_info.has_color ? 1u : 0u) | (g.vdb_info.has_emission ? 2u : 0u);
-        r.density_tex = g.vdb_info.density_texture; r.emission_tex = g.vdb_info.emission_texture; r.color_tex = g.vdb_info.color_texture;
-        vrec[v] = r;
-    }
+    // per-volume world->index affine
+    for (int v = tid; v < N && v < max_volumes; v += nthreads) vrec[v] = make_volume_rec(vols[v]);
 }
 
 // =====================================================================================================
@@ -457,7 +465,15 @@ __global__ void k_unpermute(const uint8_t* __restrict__ gathered, uint8_t* __res
 cudaError_t launch_prepare_scene(const vpt_gpu_vdb* vols, const vpt_octnode* root, SceneTables* out, OctInternal* internal,
                                  uint2* leaf_list, int* leaf_indices, VolumeRec* vrec, int max_volumes, cudaStream_t s)
 {
-    k_prepare_scene<<<4, 256, 0, s>>>(vols, root, out, internal, leaf_list, leaf_indices, vrec, max_volumes);
+    SceneTables none; memset(&none, 0, sizeof(none));
+    k_prepare_scene<<<4, 256, 0, s>>>(vols, root, out, internal, leaf_list, leaf_indices, vrec, max_volumes, none);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prepare_volumes(const vpt_gpu_vdb* vols, const SceneTables& hdr, SceneTables* out, VolumeRec* vrec, cudaStream_t s)
+{
+    const int blocks = hdr.num_volumes > 4096 ? 32 : 4;
+    k_prepare_scene<<<blocks, 256, 0, s>>>(vols, nullptr, out, nullptr, nullptr, nullptr, vrec, hdr.num_volumes, hdr);
     return cudaGetLastError();
 }
 
@@ -476,12 +492,6 @@ static size_t trace_smem_bytes() { return (size_t)kTraceWarps * kRayWords * kPoo
 template <int kInteg, bool kLean>
 static cudaError_t launch_trace_t(const FrameArgs& fa, const vpt_atmosphere* atm, int n_ctas, cudaStream_t s)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_trace<kInteg, kLean>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     if constexpr (kInteg != 0) k_trace<kInteg, kLean><<<n_ctas, kTraceThreads, trace_smem_bytes(), s>>>(fa, *atm);
     else                       k_trace<kInteg, kLean><<<n_ctas, kTraceThreads, trace_smem_bytes(), s>>>(fa, NoAtmo{});
     return cudaGetLastError();
@@ -493,19 +503,22 @@ cudaError_t launch_trace(const FrameArgs& fa, const vpt_atmosphere* atm, bool le
     return lean ? launch_trace_t<0, true>(fa, nullptr, n_ctas, s) : launch_trace_t<0, false>(fa, nullptr, n_ctas, s);
 }
 
+// Once per context (= per device): opt the three instantiations into their dynamic shared memory and record how many CTAs
+// of each fit on an SM.  The attribute is a per-device property of the function, so this must not be a process-wide static.
 template <int kInteg, bool kLean>
-static int max_ctas_t()
+static cudaError_t trace_init_t(int* max_ctas)
 {
-    int n = 0;
-    cudaFuncSetAttribute(k_trace<kInteg, kLean>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<kInteg, kLean>, kTraceThreads, trace_smem_bytes());
-    return n;
+    cudaError_t e = cudaFuncSetAttribute(k_trace<kInteg, kLean>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_ctas, k_trace<kInteg, kLean>, kTraceThreads, trace_smem_bytes());
 }
 
-int trace_max_ctas_per_sm(int integrator, bool lean)
+cudaError_t trace_kernels_init(int max_ctas[3])
 {
-    if (integrator) return max_ctas_t<1, false>();
-    return lean ? max_ctas_t<0, true>() : max_ctas_t<0, false>();
+    cudaError_t e = trace_init_t<0, false>(&max_ctas[0]);
+    if (e == cudaSuccess) e = trace_init_t<0, true>(&max_ctas[1]);
+    if (e == cudaSuccess) e = trace_init_t<1, false>(&max_ctas[2]);
+    return e;
 }
 
 cudaError_t launch_resolve(const FrameArgs& fa, const vpt_atmosphere* sky, int n_passes, int sampled, int write_display, cudaStream_t s)

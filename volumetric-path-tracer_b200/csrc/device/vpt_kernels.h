@@ -49,10 +49,12 @@ struct FrameArgs {
 
 cudaError_t launch_prepare_scene(const vpt_gpu_vdb* vols, const vpt_octnode* root, SceneTables* out, OctInternal* internal,
                                  uint2* leaf_list, int* leaf_indices, VolumeRec* vrec, int max_volumes, cudaStream_t s);
+cudaError_t launch_prepare_volumes(const vpt_gpu_vdb* vols, const SceneTables& hdr, SceneTables* out, VolumeRec* vrec, cudaStream_t s);
 cudaError_t launch_generate(const FrameArgs& fa, int n_passes, cudaStream_t s);
 // atm != null selects the volumetric path integrator variant of the trace kernel
 cudaError_t launch_trace(const FrameArgs& fa, const vpt_atmosphere* atm, bool lean, int n_ctas, cudaStream_t s);
-int         trace_max_ctas_per_sm(int integrator, bool lean);
+// per device: dynamic shared memory opt-in of the three k_trace instantiations + CTAs per SM of [generic, lean, volumetric path]
+cudaError_t trace_kernels_init(int max_ctas[3]);
 // sky != null selects the environment_type == 0 variant (host copy of the caller's AtmosphereParameters)
 cudaError_t launch_resolve(const FrameArgs& fa, const vpt_atmosphere* sky, int n_passes, int sampled, int write_display, cudaStream_t s);
 cudaError_t launch_bn_prepare(void* bn, float2* table, int np, cudaStream_t s);

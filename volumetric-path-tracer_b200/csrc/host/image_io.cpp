@@ -53,6 +53,7 @@ bool load_hdr_float4(const std::string& path, std::vector<float>& rgba, unsigned
         }
     }
     if (!W || !H) { err = "missing resolution"; return false; }
+    if (W > 65536 || H > 65536) { err = "implausible resolution"; return false; }
     if (flipY) { err = "+Y orientation not supported"; return false; }
     rgba.assign(size_t(W) * H * 4, 0.0f);
     std::vector<uint8_t> row(size_t(W) * 4);
@@ -64,7 +65,7 @@ bool load_hdr_float4(const std::string& path, std::vector<float>& rgba, unsigned
             rle = true; p += 4;
         }
         if (!rle) {
-            if (p + size_t(W) * 4 > d.size()) { err = "truncated pixels"; return false; }
+            if (size_t(W) * 4 > d.size() - p) { err = "truncated pixels"; return false; }
             memcpy(row.data(), &d[p], size_t(W) * 4); p += size_t(W) * 4;
         } else {
             for (unsigned c = 0; c < 4; ++c) {
@@ -77,7 +78,7 @@ bool load_hdr_float4(const std::string& path, std::vector<float>& rgba, unsigned
                         const uint8_t v = d[p++];
                         for (unsigned k = 0; k < num; ++k) row[(pos++) * 4 + c] = v;
                     } else {
-                        if (p + num > d.size() || pos + num > W) { err = "bad RLE literal"; return false; }
+                        if (num > d.size() - p || pos + num > W) { err = "bad RLE literal"; return false; }
                         for (unsigned k = 0; k < num; ++k) row[(pos++) * 4 + c] = d[p++];
                     }
                 }
@@ -105,7 +106,7 @@ bool load_bmp_float3_rbg(const std::string& path, std::vector<float>& xyz, int& 
     if (bpp != 24 || comp != 0 || w <= 0 || h == 0) { err = "only 24-bit uncompressed BMPs are supported"; return false; }
     const bool bottom_up = h > 0; if (h < 0) h = -h;
     const size_t stride = (size_t(w) * 3 + 3) & ~size_t(3);
-    if (off + stride * h > d.size()) { err = "truncated BMP"; return false; }
+    if (w > 65536 || h > 65536 || off > d.size() || stride * size_t(h) > d.size() - off) { err = "truncated BMP"; return false; }
     W = w; H = h; xyz.resize(size_t(w) * h * 3);
     for (int y = 0; y < h; ++y) {
         const uint8_t* src = &d[off + stride * size_t(bottom_up ? h - 1 - y : y)];
@@ -124,35 +125,62 @@ bool load_exr_float3(const std::string& path, std::vector<float>& rgb, int& W, i
     if (d.size() < 8 || d[0] != 0x76 || d[1] != 0x2f || d[2] != 0x31 || d[3] != 0x01) { err = "not an OpenEXR file"; return false; }
     uint32_t ver; memcpy(&ver, &d[4], 4);
     if (ver & 0x1E00) { err = "tiled / deep / multipart EXR not supported"; return false; }
+    const size_t n = d.size();
+    // every offset below comes from the file: nothing is dereferenced before it is checked against the file size
+    auto fits = [&](size_t at, size_t k) { return at <= n && k <= n - at; };
+    auto cstr = [&](size_t& at, std::string& out) {          // NUL-terminated string inside the file
+        size_t e = at;
+        while (e < n && d[e] != 0) ++e;
+        if (e >= n) return false;
+        out.assign((const char*)&d[at], e - at); at = e + 1;
+        return true;
+    };
     size_t p = 8;
     struct Ch { std::string name; int type; };
     std::vector<Ch> chans; int comp = -1; int32_t dw[4] = {0, 0, -1, -1};
-    while (p < d.size() && d[p] != 0) {
-        std::string name((const char*)&d[p]); p += name.size() + 1;
-        std::string type((const char*)&d[p]); p += type.size() + 1;
+    for (;;) {
+        if (p >= n) { err = "truncated EXR header"; return false; }
+        if (d[p] == 0) { ++p; break; }
+        std::string name, type;
+        if (!cstr(p, name) || !cstr(p, type) || !fits(p, 4)) { err = "truncated EXR attribute"; return false; }
         uint32_t sz; memcpy(&sz, &d[p], 4); p += 4;
+        if (!fits(p, sz)) { err = "EXR attribute '" + name + "' runs past the end of the file"; return false; }
+        const size_t end = p + sz;
         if (type == "chlist") {
             size_t q = p;
-            while (d[q] != 0) { Ch c; c.name = (const char*)&d[q]; q += c.name.size() + 1; int32_t t; memcpy(&t, &d[q], 4); c.type = t; q += 16; chans.push_back(c); }
-        } else if (type == "compression") comp = d[p];
-        else if (name == "dataWindow") memcpy(dw, &d[p], 16);
-        p += sz;
+            for (;;) {
+                if (q >= end) { err = "unterminated EXR channel list"; return false; }
+                if (d[q] == 0) break;
+                Ch c; size_t e = q;
+                while (e < end && d[e] != 0) ++e;
+                if (e >= end || end - (e + 1) < 16) { err = "truncated EXR channel entry"; return false; }
+                c.name.assign((const char*)&d[q], e - q); q = e + 1;
+                int32_t t; memcpy(&t, &d[q], 4); c.type = t; q += 16;
+                if (c.type < 0 || c.type > 2) { err = "unknown EXR pixel type"; return false; }
+                chans.push_back(c);
+            }
+        } else if (type == "compression") { if (sz < 1) { err = "bad EXR compression attribute"; return false; } comp = d[p]; }
+        else if (name == "dataWindow") { if (sz < 16) { err = "bad EXR dataWindow attribute"; return false; } memcpy(dw, &d[p], 16); }
+        p = end;
     }
-    ++p;
     if (comp != 0) { err = "only uncompressed EXR is supported (compression=" + std::to_string(comp) + ")"; return false; }
-    W = dw[2] - dw[0] + 1; H = dw[3] - dw[1] + 1;
-    if (W <= 0 || H <= 0) { err = "bad dataWindow"; return false; }
+    const int64_t w64 = (int64_t)dw[2] - dw[0] + 1, h64 = (int64_t)dw[3] - dw[1] + 1;
+    if (w64 <= 0 || h64 <= 0 || w64 > 65536 || h64 > 65536) { err = "bad dataWindow"; return false; }
+    W = (int)w64; H = (int)h64;
+    if (!fits(p, size_t(H) * 8)) { err = "truncated EXR scanline offset table"; return false; }
     rgb.assign(size_t(W) * H * 3, 0.0f);
     std::vector<uint64_t> offs(H);
     memcpy(offs.data(), &d[p], size_t(H) * 8);
     for (int y = 0; y < H; ++y) {
+        if (offs[y] > n || !fits((size_t)offs[y], 8)) { err = "EXR scanline offset outside the file"; return false; }
         size_t q = (size_t)offs[y];
         int32_t yy, bytes; memcpy(&yy, &d[q], 4); memcpy(&bytes, &d[q + 4], 4); q += 8;
-        const int row = yy - dw[1];
+        const int64_t row = (int64_t)yy - dw[1];
+        if (row < 0 || row >= H) { err = "EXR scanline outside the dataWindow"; return false; }
         for (const Ch& c : chans) {                      // channels are stored in the chlist (alphabetical) order
             const int slot = c.name == "R" ? 0 : c.name == "G" ? 1 : c.name == "B" ? 2 : -1;
             const size_t esz = c.type == 1 ? 2 : 4;
-            if (q + esz * W > d.size()) { err = "truncated EXR scanline"; return false; }
+            if (!fits(q, esz * W)) { err = "truncated EXR scanline"; return false; }
             if (slot >= 0) for (int x = 0; x < W; ++x) {
                 float v;
                 if (c.type == 1) { uint16_t hv; memcpy(&hv, &d[q + 2 * size_t(x)], 2); v = half_to_float(hv); }

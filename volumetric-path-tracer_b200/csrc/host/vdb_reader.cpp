@@ -11,6 +11,8 @@
 
 #include <cstdio>
 #include <cstring>
+#include <cstdint>
+#include <climits>
 #include <cmath>
 #include <stdexcept>
 #include <algorithm>
@@ -22,7 +24,10 @@ namespace {
 struct Reader {
     const uint8_t* p; size_t n; size_t pos = 0;
     Reader(const uint8_t* p_, size_t n_) : p(p_), n(n_) {}
-    void need(size_t k) const { if (pos + k > n) throw std::runtime_error("vdb: unexpected end of file"); }
+    // overflow-safe: `pos + k` may wrap for sizes taken from the file
+    void need(size_t k) const { if (pos > n || k > n - pos) throw std::runtime_error("vdb: unexpected end of file"); }
+    // absolute seek to an offset stored in the file (grid descriptors): must lie inside the file
+    void seek(int64_t to) { if (to < 0 || (uint64_t)to > (uint64_t)n) throw std::runtime_error("vdb: stored offset outside the file"); pos = (size_t)to; }
     template <typename T> T get() { need(sizeof(T)); T v; memcpy(&v, p + pos, sizeof(T)); pos += sizeof(T); return v; }
     void read(void* dst, size_t k) { need(k); memcpy(dst, p + pos, k); pos += k; }
     void skip(size_t k) { need(k); pos += k; }
@@ -36,7 +41,7 @@ size_t lz4_block_decode(const uint8_t* src, size_t srcLen, uint8_t* dst, size_t 
         unsigned token = src[ip++];
         size_t lit = token >> 4;
         if (lit == 15) { unsigned b; do { if (ip >= srcLen) throw std::runtime_error("lz4: truncated literal length"); b = src[ip++]; lit += b; } while (b == 255); }
-        if (ip + lit > srcLen || op + lit > dstCap) throw std::runtime_error("lz4: literal overrun");
+        if (lit > srcLen - ip || lit > dstCap - op) throw std::runtime_error("lz4: literal overrun");
         memcpy(dst + op, src + ip, lit); ip += lit; op += lit;
         if (ip >= srcLen) break;                       // last sequence has no match part
         if (ip + 2 > srcLen) throw std::runtime_error("lz4: truncated offset");
@@ -45,7 +50,7 @@ size_t lz4_block_decode(const uint8_t* src, size_t srcLen, uint8_t* dst, size_t 
         size_t mlen = token & 15;
         if (mlen == 15) { unsigned b; do { if (ip >= srcLen) throw std::runtime_error("lz4: truncated match length"); b = src[ip++]; mlen += b; } while (b == 255); }
         mlen += 4;
-        if (op + mlen > dstCap) throw std::runtime_error("lz4: match overrun");
+        if (mlen > dstCap - op) throw std::runtime_error("lz4: match overrun");
         for (size_t i = 0; i < mlen; ++i) dst[op + i] = dst[op - off + i];   // may overlap
         op += mlen;
     }
@@ -66,7 +71,10 @@ void blosc1_decode(const uint8_t* f, size_t flen, uint8_t* out, size_t outLen) {
     if (memcpyed) { if (16 + size_t(nbytes) > flen) throw std::runtime_error("blosc: short memcpy frame"); memcpy(out, f + 16, nbytes); return; }
     if (codec != 1) throw std::runtime_error("blosc: only the LZ4 codec is supported");
     if (blocksize == 0) throw std::runtime_error("blosc: zero blocksize");
-    const uint32_t nblocks = (nbytes + blocksize - 1) / blocksize;
+    if (typesize == 0) throw std::runtime_error("blosc: zero typesize");
+    if (blocksize > (1u << 30)) throw std::runtime_error("blosc: implausible blocksize");
+    const uint32_t nblocks = (uint32_t)(((uint64_t)nbytes + blocksize - 1) / blocksize);
+    if (16 + 4 * (uint64_t)nblocks > flen) throw std::runtime_error("blosc: block-start table does not fit the frame");
     std::vector<uint8_t> tmp(blocksize);
     for (uint32_t b = 0; b < nblocks; ++b) {
         int32_t bstart; memcpy(&bstart, f + 16 + 4 * b, 4);
@@ -74,12 +82,13 @@ void blosc1_decode(const uint8_t* f, size_t flen, uint8_t* out, size_t outLen) {
         const bool leftover = (bsize != blocksize);
         const unsigned nsplits = (!dontsplit && typesize <= 16 && blocksize / typesize >= 128 && !leftover) ? typesize : 1;
         const uint32_t neblock = bsize / nsplits;
+        if (bstart < 16 || (size_t)bstart > flen) throw std::runtime_error("blosc: bad block start");
         size_t ip = (size_t)bstart;
         uint8_t* dstb = shuffle ? tmp.data() : out + size_t(b) * blocksize;
         for (unsigned s = 0; s < nsplits; ++s) {
-            if (ip + 4 > flen) throw std::runtime_error("blosc: truncated stream header");
+            if (ip > flen || 4 > flen - ip) throw std::runtime_error("blosc: truncated stream header");
             int32_t csize; memcpy(&csize, f + ip, 4); ip += 4;
-            if (csize < 0 || ip + (size_t)csize > flen) throw std::runtime_error("blosc: bad stream size");
+            if (csize < 0 || (size_t)csize > flen - ip) throw std::runtime_error("blosc: bad stream size");
             if ((uint32_t)csize == neblock) memcpy(dstb + size_t(s) * neblock, f + ip, neblock);
             else if (lz4_block_decode(f + ip, csize, dstb + size_t(s) * neblock, neblock) != neblock)
                 throw std::runtime_error("blosc: LZ4 stream decoded to the wrong length");
@@ -106,7 +115,7 @@ void read_data(Reader& r, const Ctx& c, uint8_t* dst, uint32_t count) {
     const size_t bytes = size_t(count) * c.vsize;
     if (c.compression & COMPRESS_BLOSC) {
         int64_t nb = r.get<int64_t>();
-        if (nb <= 0) { if (size_t(-nb) != bytes) throw std::runtime_error("vdb: raw payload size mismatch"); r.read(dst, bytes); }
+        if (nb <= 0) { if (nb == INT64_MIN || uint64_t(-nb) != bytes) throw std::runtime_error("vdb: raw payload size mismatch"); r.read(dst, bytes); }
         else { r.need((size_t)nb); blosc1_decode(r.p + r.pos, (size_t)nb, dst, bytes); r.pos += (size_t)nb; }
     } else if (c.compression & COMPRESS_ZIP) {
         int64_t nb = r.get<int64_t>();
@@ -136,6 +145,7 @@ void read_compressed_values(Reader& r, const Ctx& c, uint8_t* dst, uint32_t coun
     else if (c.compression & (COMPRESS_BLOSC | COMPRESS_ZIP)) {
         // zero-value payloads still carry the int64 size word, and Blosc emits a bare 16-byte frame header for them
         int64_t nb = r.get<int64_t>();
+        if (nb == INT64_MIN) throw std::runtime_error("vdb: bad payload size");
         r.skip((size_t)(nb < 0 ? -nb : nb));
     }
     uint32_t ti = 0;
@@ -206,7 +216,7 @@ std::vector<std::string> vdb_list_grids(const uint8_t* data, size_t n) {
     r.skip(8); r.skip(1); r.skip(36); skip_metamap(r, nullptr);
     uint32_t gc = r.get<uint32_t>();
     std::vector<std::string> out;
-    for (uint32_t g = 0; g < gc; ++g) { std::string nm = r.str(); r.str(); r.str(); r.skip(16); int64_t endPos = r.get<int64_t>(); out.push_back(nm); r.pos = (size_t)endPos; }
+    for (uint32_t g = 0; g < gc; ++g) { std::string nm = r.str(); r.str(); r.str(); r.skip(16); int64_t endPos = r.get<int64_t>(); out.push_back(nm); r.seek(endPos); }
     return out;
 }
 
@@ -225,14 +235,16 @@ bool vdb_read_dense(const uint8_t* data, size_t n, const std::string& grid_name,
         int64_t gridPos = r.get<int64_t>(), blockPos = r.get<int64_t>(), endPos = r.get<int64_t>();
         // OpenVDB appends "\x1e<n>" to duplicate names; compare the visible part
         std::string vis = name.substr(0, name.find('\x1e'));
-        if (vis != grid_name) { r.pos = (size_t)endPos; continue; }
+        if (gridPos < 0 || blockPos < gridPos || endPos < blockPos || (uint64_t)endPos > (uint64_t)n)
+            throw std::runtime_error("vdb: grid descriptor offsets are inconsistent with the file size");
+        if (vis != grid_name) { r.seek(endPos); continue; }
 
         Ctx c;
         if (type == "Tree_float_5_4_3") c.vsize = 4;
         else if (type == "Tree_vec3s_5_4_3") c.vsize = 12;
         else throw std::runtime_error("vdb: unsupported grid type " + type);
         out.channels = c.vsize / 4;
-        r.pos = (size_t)gridPos;
+        r.seek(gridPos);
         c.compression = r.get<uint32_t>();
         out.meta = VdbGridMeta();
         skip_metamap(r, &out.meta);
@@ -259,12 +271,19 @@ bool vdb_read_dense(const uint8_t* data, size_t n, const std::string& grid_name,
         if (r.get<uint32_t>() != 1) throw std::runtime_error("vdb: multi-buffer trees not supported");
         c.background.resize(c.vsize); r.read(c.background.data(), c.vsize);
         const uint32_t numTiles = r.get<uint32_t>(), numChildren = r.get<uint32_t>();
+        // every root tile / child record occupies at least 13 bytes of the file: reject counts the file cannot hold
+        if ((uint64_t)numTiles * 13 > n || (uint64_t)numChildren * 13 > n) throw std::runtime_error("vdb: root table larger than the file");
         TreeTopo topo;
         for (uint32_t i = 0; i < numTiles; ++i) {
-            Tile t; r.read(t.o, 12); t.size = 4096; t.value.resize(c.vsize); r.read(t.value.data(), c.vsize); t.active = r.get<uint8_t>() != 0;
+            Tile t; r.read(t.o, 12); t.size = 4096;
+            for (int a = 0; a < 3; ++a) if (t.o[a] < -(1 << 30) || t.o[a] > (1 << 30)) throw std::runtime_error("vdb: root tile origin out of range"); t.value.resize(c.vsize); r.read(t.value.data(), c.vsize); t.active = r.get<uint8_t>() != 0;
             topo.tiles.push_back(std::move(t));
         }
-        for (uint32_t i = 0; i < numChildren; ++i) { int32_t o[3]; r.read(o, 12); read_internal5(r, c, o, topo); }
+        for (uint32_t i = 0; i < numChildren; ++i) {
+            int32_t o[3]; r.read(o, 12);
+            for (int a = 0; a < 3; ++a) if (o[a] < -(1 << 30) || o[a] > (1 << 30)) throw std::runtime_error("vdb: root child origin out of range");
+            read_internal5(r, c, o, topo);
+        }
         if ((int64_t)r.pos != blockPos) throw std::runtime_error("vdb: topology did not end at blockPos");
 
         // leaf buffers
@@ -286,13 +305,24 @@ bool vdb_read_dense(const uint8_t* data, size_t n, const std::string& grid_name,
                 ++active;
             }
         for (const Tile& t : topo.tiles) if (t.active) {
-            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], t.o[a]); hi[a] = std::max(hi[a], t.o[a] + t.size - 1); }
+            for (int a = 0; a < 3; ++a) {
+                const int64_t top = (int64_t)t.o[a] + t.size - 1;
+                if (top > INT32_MAX) throw std::runtime_error("vdb: tile origin out of range");
+                lo[a] = std::min(lo[a], t.o[a]); hi[a] = std::max(hi[a], (int32_t)top);
+            }
             tileVox += uint64_t(t.size) * t.size * t.size; ++activeTiles;
         }
         if (active + tileVox == 0) throw std::runtime_error("vdb: grid has no active voxels");
         out.leaf_count = (uint32_t)topo.leaves.size(); out.active_leaf_voxels = active; out.active_tiles = activeTiles; out.active_tile_voxels = tileVox;
         memcpy(out.bbox_min, lo, 12); memcpy(out.bbox_max, hi, 12);
-        for (int a = 0; a < 3; ++a) out.dim[a] = hi[a] - lo[a] + 1;
+        // the dense box must stay addressable: cap each edge and the voxel count before allocating (16 Gi voxels = 64 GiB of float)
+        uint64_t voxels = 1;
+        for (int a = 0; a < 3; ++a) {
+            const int64_t d = (int64_t)hi[a] - (int64_t)lo[a] + 1;
+            if (d < 1 || d > 65536) throw std::runtime_error("vdb: active bounding box edge outside 1..65536 voxels");
+            out.dim[a] = (int32_t)d; voxels *= (uint64_t)d;
+        }
+        if (voxels > (1ull << 34)) throw std::runtime_error("vdb: active bounding box holds more than 2^34 voxels");
         memcpy(out.background, c.background.data(), c.vsize);
 
         // dense fill (copyToDense: every voxel of the box takes the tree's value there)
@@ -302,10 +332,10 @@ bool vdb_read_dense(const uint8_t* data, size_t n, const std::string& grid_name,
           for (size_t i = 0; i < nx * ny * nz; ++i) for (size_t k = 0; k < ch; ++k) out.values[i * ch + k] = bg[k]; }
         auto fill_box = [&](const int32_t o[3], int32_t size, const uint8_t* v) {
             float val[3]; memcpy(val, v, c.vsize);
-            const int32_t x0 = std::max(o[0], lo[0]), x1 = std::min(o[0] + size - 1, hi[0]);
-            const int32_t y0 = std::max(o[1], lo[1]), y1 = std::min(o[1] + size - 1, hi[1]);
-            const int32_t z0 = std::max(o[2], lo[2]), z1 = std::min(o[2] + size - 1, hi[2]);
-            for (int32_t z = z0; z <= z1; ++z) for (int32_t y = y0; y <= y1; ++y) for (int32_t x = x0; x <= x1; ++x) {
+            const int64_t x0 = std::max<int64_t>(o[0], lo[0]), x1 = std::min<int64_t>((int64_t)o[0] + size - 1, hi[0]);
+            const int64_t y0 = std::max<int64_t>(o[1], lo[1]), y1 = std::min<int64_t>((int64_t)o[1] + size - 1, hi[1]);
+            const int64_t z0 = std::max<int64_t>(o[2], lo[2]), z1 = std::min<int64_t>((int64_t)o[2] + size - 1, hi[2]);
+            for (int64_t z = z0; z <= z1; ++z) for (int64_t y = y0; y <= y1; ++y) for (int64_t x = x0; x <= x1; ++x) {
                 const size_t idx = (size_t(z - lo[2]) * ny + size_t(y - lo[1])) * nx + size_t(x - lo[0]);
                 for (size_t k = 0; k < ch; ++k) out.values[idx * ch + k] = val[k];
             }

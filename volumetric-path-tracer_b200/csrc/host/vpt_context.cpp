@@ -7,8 +7,7 @@
 //        memset(queue counters) -> k_bn_prepare -> k_generate -> k_trace<integrator, lean> (persistent) -> k_resolve<env>
 //   passes beyond max_interactions / render == false: k_resolve (re-tonemap) + k_bn_advance
 // which leaves every buffer named by Kernel_params in the state n reference launches would.
-#include "../../../include/vpt_b200.h"
-#include "../device/vpt_kernels.h"
+#include "vpt_host.h"
 #include "vdb_reader.h"
 #include "image_io.h"
 
@@ -25,13 +24,8 @@
 #include <algorithm>
 #include <vector>
 
-namespace vpt {
-cudaError_t octree_build_device(vpt_octnode* d_nodes, const vpt_gpu_vdb* d_vols, int n, cudaStream_t s);
-void instance_bounds_host(const vpt_gpu_vdb& g, float out6[6]);
-cudaError_t octree_snapshot(const vpt_octnode* d_root, vpt_octnode* h_nodes, int* h_exists);
-}
-
 static thread_local std::string g_last_error;
+namespace vpt { int fail_global(int code, const std::string& msg) { g_last_error = msg; return code; } }
 
 struct vpt_context {
     int device = 0;
@@ -42,9 +36,14 @@ struct vpt_context {
     int ctas_per_sm = 0;
     // partition
     int rank = 0, n_ranks = 1, stripe_rows = 16;
-    // scene cache
+    // scene cache: keyed by the two device pointers AND the registry generation of the octree (a rebuilt octree that got the
+    // same address back is a different scene); the cheap per-volume records are refreshed whenever a new frame starts
     vpt_devptr_t cached_volumes = 0, cached_root = 0;
+    unsigned long long cached_generation = 0;
     bool   scene_single_volume = false;
+    size_t cap_vrec = 0;              // VolumeRec capacity (grows with the instance count)
+    int*   h_pinned = nullptr;        // one pinned word for the 4-byte read-back a foreign octree needs
+    int    max_ctas[3] = {0, 0, 0};   // k_trace occupancy per instantiation: [0] generic, [1] lean, [2] volumetric path
     int    force_generic = 0;        // option "generic_kernel": 1 = never use the lean trace instantiation (A/B and tests)
     vpt::SceneTables* d_scene = nullptr;
     vpt::OctInternal* d_internal = nullptr;
@@ -106,6 +105,17 @@ int vpt_abi_sizes(size_t* out, int n) {
 
 const char* vpt_last_error(const vpt_context* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 
+static void free_context(vpt_context* c) {
+    if (!c) return;
+    cudaFree(c->d_scene); cudaFree(c->d_internal); cudaFree(c->d_leaf_list); cudaFree(c->d_leaf_indices); cudaFree(c->d_vrec);
+    cudaFree(c->d_stats);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    cudaFree(c->d_queue_id); cudaFree(c->d_queue_org); cudaFree(c->d_bn_table);
+    cudaFree(c->d_counters); cudaFree(c->d_queue); cudaFree(c->d_planeA); cudaFree(c->d_planeB); cudaFree(c->d_planeC); cudaFree(c->d_planeD);
+    delete c;
+}
+
 int vpt_create(vpt_context** out) {
     if (!out) return fail(nullptr, VPT_ERR_INVALID, "vpt_create: null output pointer");
     *out = nullptr;
@@ -114,32 +124,27 @@ int vpt_create(vpt_context** out) {
     if (e != cudaSuccess || ndev == 0)
         return fail(nullptr, VPT_ERR_CUDA, std::string("vpt_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
     vpt_context* c = new vpt_context();
-    VPT_CUDA(c, cudaGetDevice(&c->device));
+    // every failure below releases what was allocated so far (the context never escapes half-built)
+#define VPT_CREATE(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+        const std::string m_ = std::string("vpt_create: " #call ": ") + cudaGetErrorString(e_); free_context(c); return fail(nullptr, VPT_ERR_CUDA, m_); } } while (0)
+    VPT_CREATE(cudaGetDevice(&c->device));
     cudaDeviceProp prop;
-    VPT_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
-    if (prop.major < 10) { std::string m = "vpt_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ", kernels are built for sm_100a only"; delete c; return fail(nullptr, VPT_ERR_UNSUPPORTED, m); }
+    VPT_CREATE(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major < 10) { std::string m = "vpt_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ", kernels are built for sm_100a only"; free_context(c); return fail(nullptr, VPT_ERR_UNSUPPORTED, m); }
     c->num_sms = prop.multiProcessorCount;
-    VPT_CUDA(c, cudaMalloc(&c->d_scene, sizeof(vpt::SceneTables)));
-    VPT_CUDA(c, cudaMalloc(&c->d_internal, sizeof(vpt::OctInternal) * vpt::kOctInternalNodes));
-    VPT_CUDA(c, cudaMalloc(&c->d_leaf_list, sizeof(uint2) * vpt::kOctLeaves));
-    VPT_CUDA(c, cudaMalloc(&c->d_leaf_indices, sizeof(int) * vpt::kOctLeaves * VPT_OCT_MAX_VOLUMES));
-    VPT_CUDA(c, cudaMalloc(&c->d_vrec, sizeof(vpt::VolumeRec) * VPT_OCT_MAX_VOLUMES));
-    VPT_CUDA(c, cudaMalloc(&c->d_counters, sizeof(unsigned) * 4));
-    VPT_CUDA(c, cudaMalloc(&c->d_stats, sizeof(unsigned long long) * 8));
-    VPT_CUDA(c, cudaMemset(c->d_stats, 0, sizeof(unsigned long long) * 8));
+    VPT_CREATE(cudaMalloc(&c->d_scene, sizeof(vpt::SceneTables)));
+    VPT_CREATE(cudaMalloc(&c->d_counters, sizeof(unsigned) * 4));
+    VPT_CREATE(cudaMalloc(&c->d_stats, sizeof(unsigned long long) * 8));
+    VPT_CREATE(cudaMemset(c->d_stats, 0, sizeof(unsigned long long) * 8));
+    VPT_CREATE(cudaHostAlloc((void**)&c->h_pinned, sizeof(int) * 4, cudaHostAllocDefault));
+    // per-DEVICE kernel attributes (dynamic shared memory opt-in) and the occupancy the persistent grid is sized with
+    VPT_CREATE(vpt::trace_kernels_init(c->max_ctas));
+#undef VPT_CREATE
     *out = c;
     return VPT_OK;
 }
 
-void vpt_destroy(vpt_context* c) {
-    if (!c) return;
-    cudaFree(c->d_scene); cudaFree(c->d_internal); cudaFree(c->d_leaf_list); cudaFree(c->d_leaf_indices); cudaFree(c->d_vrec);
-    cudaFree(c->d_stats);
-    for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    cudaFree(c->d_queue_id); cudaFree(c->d_queue_org); cudaFree(c->d_bn_table);
-    cudaFree(c->d_counters); cudaFree(c->d_queue); cudaFree(c->d_planeA); cudaFree(c->d_planeB); cudaFree(c->d_planeC); cudaFree(c->d_planeD);
-    delete c;
-}
+void vpt_destroy(vpt_context* c) { free_context(c); }
 
 int vpt_set_option(vpt_context* c, const char* key, int value) {
     if (!c || !key) return fail(c, VPT_ERR_INVALID, "vpt_set_option: null argument");
@@ -176,7 +181,7 @@ int vpt_unpermute(vpt_context* c, const void* d_gathered, void* d_full, unsigned
 
 int vpt_invalidate_scene(vpt_context* c) {
     if (!c) return VPT_ERR_INVALID;
-    c->cached_volumes = 0; c->cached_root = 0;
+    c->cached_volumes = 0; c->cached_root = 0; c->cached_generation = 0;
     return VPT_OK;
 }
 
@@ -244,18 +249,52 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         return fail(c, VPT_ERR_INVALID, "Kernel_params output buffer pointer is null");
     if (kp.resolution.x == 0 || kp.resolution.y == 0) return fail(c, VPT_ERR_INVALID, "resolution is zero");
 
-    // scene tables (cached per pointer pair)
-    if (c->cached_volumes != d_volumes || c->cached_root != d_root) {
-        VPT_CUDA(c, vpt::launch_prepare_scene(reinterpret_cast<const vpt_gpu_vdb*>(d_volumes), reinterpret_cast<const vpt_octnode*>(d_root),
-                                              c->d_scene, c->d_internal, c->d_leaf_list, c->d_leaf_indices, c->d_vrec, VPT_OCT_MAX_VOLUMES, stream));
-        c->launches++;
-        c->cached_volumes = d_volumes; c->cached_root = d_root;
-        // one 4-byte read-back per scene: lets the host pick the trace kernel instantiation without the multi-volume code
-        int single = 0;
-        VPT_CUDA(c, cudaMemcpyAsync(&single, reinterpret_cast<const char*>(c->d_scene) + offsetof(vpt::SceneTables, single_volume), sizeof(int),
-                                    cudaMemcpyDeviceToHost, stream));
-        VPT_CUDA(c, cudaStreamSynchronize(stream));
-        c->scene_single_volume = single != 0;
+    // ---- scene tables ---------------------------------------------------------------------------------------
+    // Octrees built by vpt_octree_build are registered with their flat tables and instance count: nothing is read
+    // back and nothing blocks.  A foreign (reference-built, pointer-linked) octree is flattened on the device and
+    // its instance count read back (4 bytes, one stream synchronisation) when the pointers change or a frame starts.
+    {
+        vpt::SceneEntry ent;
+        const bool registered = vpt::scene_registry_find(d_root, &ent);
+        if (registered && ent.device != c->device) return fail(c, VPT_ERR_INVALID, "octree was built on another device");
+        const bool key_changed = c->cached_volumes != d_volumes || c->cached_root != d_root || c->cached_generation != (registered ? ent.generation : 0ull);
+        // iteration == 0 starts a new frame: every scene edit of the reference application resets it (main.cpp:1667-1780), so
+        // refreshing the cheap tables there also covers buffers that were rewritten or reallocated at the same address
+        if (key_changed || kp.iteration == 0) {
+            if (registered) {
+                if ((size_t)ent.n > c->cap_vrec) {
+                    cudaFree(c->d_vrec); c->d_vrec = nullptr; c->cap_vrec = 0;
+                    VPT_CUDA(c, cudaMalloc(&c->d_vrec, sizeof(vpt::VolumeRec) * (size_t)ent.n));
+                    c->cap_vrec = (size_t)ent.n;
+                }
+                vpt::SceneTables hdr;
+                for (int a = 0; a < 3; ++a) { hdr.root_pmin[a] = ent.root6[a]; hdr.root_pmax[a] = ent.root6[3 + a]; }
+                hdr.max_extinction = ent.max_extinction; hdr.min_extinction = ent.min_extinction;
+                hdr.num_volumes = ent.n; hdr.single_volume = ent.n == 1 ? 1 : 0;
+                hdr.internal = ent.d_internal; hdr.leaf_list = ent.d_leaf_list; hdr.leaf_indices = ent.d_leaf_indices; hdr.volumes = c->d_vrec;
+                VPT_CUDA(c, vpt::launch_prepare_volumes(reinterpret_cast<const vpt_gpu_vdb*>(d_volumes), hdr, c->d_scene, c->d_vrec, stream));
+                c->scene_single_volume = ent.n == 1;
+            } else {
+                if (!c->d_internal) {
+                    VPT_CUDA(c, cudaMalloc(&c->d_internal, sizeof(vpt::OctInternal) * vpt::kOctInternalNodes));
+                    VPT_CUDA(c, cudaMalloc(&c->d_leaf_list, sizeof(uint2) * vpt::kOctLeaves));
+                    VPT_CUDA(c, cudaMalloc(&c->d_leaf_indices, sizeof(int) * vpt::kOctLeaves * VPT_OCT_MAX_VOLUMES));
+                }
+                if (c->cap_vrec < VPT_OCT_MAX_VOLUMES) {
+                    cudaFree(c->d_vrec); c->d_vrec = nullptr; c->cap_vrec = 0;
+                    VPT_CUDA(c, cudaMalloc(&c->d_vrec, sizeof(vpt::VolumeRec) * VPT_OCT_MAX_VOLUMES));
+                    c->cap_vrec = VPT_OCT_MAX_VOLUMES;
+                }
+                VPT_CUDA(c, vpt::launch_prepare_scene(reinterpret_cast<const vpt_gpu_vdb*>(d_volumes), reinterpret_cast<const vpt_octnode*>(d_root),
+                                                      c->d_scene, c->d_internal, c->d_leaf_list, c->d_leaf_indices, c->d_vrec, VPT_OCT_MAX_VOLUMES, stream));
+                VPT_CUDA(c, cudaMemcpyAsync(c->h_pinned, reinterpret_cast<const char*>(c->d_scene) + offsetof(vpt::SceneTables, single_volume), sizeof(int),
+                                            cudaMemcpyDeviceToHost, stream));
+                VPT_CUDA(c, cudaStreamSynchronize(stream));
+                c->scene_single_volume = c->h_pinned[0] != 0;
+            }
+            c->launches++;
+            c->cached_volumes = d_volumes; c->cached_root = d_root; c->cached_generation = registered ? ent.generation : 0ull;
+        }
     }
     // "lean" = nothing but one volume, sun and environment in play (the headline configuration)
     const bool lean = c->scene_single_volume && !(kp.emission_scale > 0.0f) && fa.lights.num_lights == 0 && kp.integrator == 0 && !c->force_generic;
@@ -288,7 +327,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
     fa.queue_count = c->d_counters; fa.queue_head = c->d_counters + 1;
     fa.planeA = c->d_planeA; fa.planeB = c->d_planeB; fa.planeC = c->d_planeC; fa.planeD = planeD ? c->d_planeD : nullptr;
 
-    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : vpt::trace_max_ctas_per_sm(vol_integ ? 1 : 0, lean);
+    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : c->max_ctas[vol_integ ? 2 : (lean ? 1 : 0)];
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int trace_ctas = c->num_sms * ctas_per_sm;
 
@@ -579,53 +618,6 @@ int vpt_exr_load_rgb(const char* path, float** rgb_out, int* w, int* h) {
     *rgb_out = (float*)malloc(px.size() * sizeof(float)); memcpy(*rgb_out, px.data(), px.size() * sizeof(float));
     return VPT_OK;
 }
-
-void vpt_volume_bounds(const vpt_gpu_vdb* v, float out6[6]) { vpt::instance_bounds_host(*v, out6); }
-
-int vpt_octree_build(const vpt_gpu_vdb* h_volumes, int n, vpt_devptr_t* d_root_out) {
-    if (!h_volumes || !d_root_out || n < 1) return fail(nullptr, VPT_ERR_INVALID, "vpt_octree_build: bad arguments");
-    if (n > VPT_OCT_MAX_VOLUMES) return fail(nullptr, VPT_ERR_UNSUPPORTED, "vpt_octree_build: more than 600 instances do not fit the reference OCTNode layout");
-    // root exactly as the reference host code builds it (union of instance bounds, +-1 world unit)
-    vpt_octnode* root = (vpt_octnode*)calloc(1, sizeof(vpt_octnode));
-    root->bbox.pmin = { 3.402823466e+38F, 3.402823466e+38F, 3.402823466e+38F };
-    root->bbox.pmax = { -3.402823466e+38F, -3.402823466e+38F, -3.402823466e+38F };
-    root->max_extinction = .0f; root->min_extinction = 3.402823466e+38F; root->voxel_size = 3.402823466e+38F;
-    root->depth = 4;
-    for (int i = 0; i < n; ++i) {
-        float b[6]; vpt::instance_bounds_host(h_volumes[i], b);
-        root->bbox.pmax.x = fmaxf(root->bbox.pmax.x, b[3]); root->bbox.pmax.y = fmaxf(root->bbox.pmax.y, b[4]); root->bbox.pmax.z = fmaxf(root->bbox.pmax.z, b[5]);
-        root->bbox.pmin.x = fminf(root->bbox.pmin.x, b[0]); root->bbox.pmin.y = fminf(root->bbox.pmin.y, b[1]); root->bbox.pmin.z = fminf(root->bbox.pmin.z, b[2]);
-        root->vol_indices[i] = i;
-        root->num_volumes++;
-        root->max_extinction = fmaxf(root->max_extinction, h_volumes[i].vdb_info.max_density);
-        root->min_extinction = fminf(root->min_extinction, h_volumes[i].vdb_info.min_density);
-        root->has_children = 1;
-    }
-    root->bbox.pmax.x += 1.0f; root->bbox.pmax.y += 1.0f; root->bbox.pmax.z += 1.0f;
-    root->bbox.pmin.x -= 1.0f; root->bbox.pmin.y -= 1.0f; root->bbox.pmin.z -= 1.0f;
-
-    vpt_octnode* d_nodes = nullptr; vpt_gpu_vdb* d_vols = nullptr;
-    cudaError_t e = cudaMalloc(&d_nodes, sizeof(vpt_octnode) * 585);
-    if (e == cudaSuccess) e = cudaMemset(d_nodes, 0, sizeof(vpt_octnode) * 585);
-    if (e == cudaSuccess) e = cudaMemcpy(d_nodes, root, sizeof(vpt_octnode), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&d_vols, sizeof(vpt_gpu_vdb) * (size_t)n);
-    if (e == cudaSuccess) e = cudaMemcpy(d_vols, h_volumes, sizeof(vpt_gpu_vdb) * (size_t)n, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = vpt::octree_build_device(d_nodes, d_vols, n, 0);
-    free(root);
-    cudaFree(d_vols);
-    if (e != cudaSuccess) { cudaFree(d_nodes); return fail(nullptr, VPT_ERR_CUDA, std::string("vpt_octree_build: ") + cudaGetErrorString(e)); }
-    *d_root_out = (vpt_devptr_t)(uintptr_t)d_nodes;
-    return VPT_OK;
-}
-
-int vpt_octree_read(vpt_devptr_t d_root, vpt_octnode* h_nodes585, int* h_exists585) {
-    if (!d_root || !h_nodes585 || !h_exists585) return fail(nullptr, VPT_ERR_INVALID, "vpt_octree_read: null argument");
-    cudaError_t e = vpt::octree_snapshot(reinterpret_cast<const vpt_octnode*>((uintptr_t)d_root), h_nodes585, h_exists585);
-    if (e != cudaSuccess) return fail(nullptr, VPT_ERR_CUDA, std::string("vpt_octree_read: ") + cudaGetErrorString(e));
-    return VPT_OK;
-}
-
-int vpt_octree_destroy(vpt_devptr_t d_root) { if (d_root) cudaFree((void*)(uintptr_t)d_root); return VPT_OK; }
 
 void vpt_camera_look_at(vpt_camera* cam, const float lookfrom[3], const float lookat[3], const float vup[3], float vfov, float aspect, float aperture) {
     auto sub = [](const float* a, const float* b, float* o) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; };

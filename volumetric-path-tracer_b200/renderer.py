@@ -45,7 +45,7 @@ class LaunchParams:
         self.p_vol = C.c_uint64(scene.d_volumes.data_ptr())
         self.p_sphere = C.c_uint64(scene.d_sphere.data_ptr())
         self.p_geo = C.c_uint64(scene.d_geo_list.data_ptr())
-        self.p_bvh = C.c_uint64(scene.d_bvh.data_ptr())
+        self.p_bvh = C.c_uint64(scene.bvh[0] if getattr(scene, "bvh", None) else scene.d_bvh.data_ptr())
         self.p_oct = C.c_uint64(scene.d_oct_root)
         self.atmos = scene.atmos
         self.array = (C.c_void_p * 9)(

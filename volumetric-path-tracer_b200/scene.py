@@ -363,6 +363,30 @@ class Scene:
         self.atmos.scattering_texture = self._dummy3d.tex; self.atmos.single_mie_scattering_texture = self._dummy3d.tex
         self.atmos.bottom_radius = 6360.0; self.atmos.top_radius = 6420.0
 
+    def octree_info(self):
+        n = C.c_int(0); ref = C.c_int(0); tot = C.c_longlong(0); mx = C.c_int(0)
+        check(lib.vpt_octree_info(self.d_oct_root, C.byref(n), C.byref(ref), C.byref(tot), C.byref(mx)), None, "vpt_octree_info")
+        return dict(n=n.value, reference_layout=bool(ref.value), total_leaf_entries=tot.value, max_leaf_entries=mx.value)
+
+    def leaf_lists(self):
+        """The flat (CSR) leaf lists the render kernels read: list of 512 ascending instance-id lists."""
+        tab = (C.c_uint * 1024)()
+        check(lib.vpt_octree_read_flat(self.d_oct_root, tab, None, 0), None, "vpt_octree_read_flat")
+        total = sum(tab[2 * l + 1] for l in range(512))
+        idx = (C.c_int * max(total, 1))()
+        check(lib.vpt_octree_read_flat(self.d_oct_root, tab, idx, total), None, "vpt_octree_read_flat")
+        return [list(idx[tab[2 * l]:tab[2 * l] + tab[2 * l + 1]]) for l in range(512)]
+
+    def build_bvh(self):
+        """LBVH over the instances in the reference's BVHNode layout (vpt_bvh_build); keeps the device arrays alive in
+        self.bvh and points params[5] (`root_node`) at them.  Returns the host view (pointers as indices)."""
+        n = len(self.instances)
+        nodes = C.c_uint64(0); leaves = C.c_uint64(0); sb = (C.c_float * 6)()
+        codes = (C.c_ulonglong * n)(); ids = (C.c_int * n)()
+        check(lib.vpt_bvh_build(self.h_volumes, n, C.byref(nodes), C.byref(leaves), sb, codes, ids), None, "vpt_bvh_build")
+        self.bvh = (nodes.value, leaves.value)
+        return read_bvh(nodes.value, leaves.value, n) | dict(scene_bounds=list(sb), codes=list(codes), ids=list(ids), d_nodes=nodes.value, d_leaves=leaves.value)
+
     def reset_blue_noise(self):
         self.d_blue_noise.copy_(torch.from_numpy(self.bn_host))
 
@@ -390,8 +414,21 @@ class Scene:
     def destroy(self):
         if self.own_octree and self.d_oct_root:
             lib.vpt_octree_destroy(self.d_oct_root); self.d_oct_root = 0
+        if getattr(self, "bvh", None):
+            lib.vpt_bvh_destroy(*self.bvh); self.bvh = None
         for t in (self.env_tex, self._dummy2d, self._dummy3d):
             if t: t.destroy()
+
+
+def read_bvh(d_nodes, d_leaves, n):
+    """Host view of a BVH in the reference layout (either builder's): child / parent fields as indices (-1 = none)."""
+    hn = (N.BVHNode * max(n - 1, 1))(); hl = (N.BVHNode * n)()
+    check(lib.vpt_bvh_read(d_nodes, d_leaves, n, hn, hl), None, "vpt_bvh_read")
+    def view(b, leaf):
+        sx = lambda v: -1 if v == 0xffffffffffffffff else int(v)
+        return dict(minId=b.minId, maxId=b.maxId, volIndex=b.volIndex, left=sx(b.leftChild), right=sx(b.rightChild), parent=sx(b.parent),
+                    box=bytes(b.boundingBox), leaf=leaf)
+    return dict(nodes=[view(hn[i], False) for i in range(n - 1)], leaves=[view(hl[i], True) for i in range(n)])
 
 
 def default_kernel_params() -> N.Kernel_params:
