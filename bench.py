@@ -1,17 +1,20 @@
 #!/usr/bin/env python3
-"""bench.py -- Msamples/s (pixels x spp) of the volumetric render pass on dragon.vdb 1920x1080.
+"""bench.py -- Msamples/s (pixels x spp) of the volumetric render pass, BASELINE.json's metric.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config C]
 
-One "step" = one 64-spp frame of BASELINE.json configs[1] (dragon.vdb, 1920x1080, ray_depth 100,
-volume_depth 1, direct integrator, sun + HDRI environment): 132.7 M samples.
-  * ours      : vpt_render_passes(64) through the C ABI (libvpt_b200.so); N > 1 shards the frame by
-                interleaved row stripes over N ranks + one NCCL all-gather of the accumulators per step.
-  * reference : the reference's own `volume_rt_kernel` (oracle/_ref, compiled from /root/reference),
-                launched as source/main.cpp:1823-1829 does: one launch + cudaDeviceSynchronize per spp.
+Default workload (the one the metric is quoted on): BASELINE.json configs[1] -- dragon.vdb, 1920x1080, 64 spp per step,
+ray_depth 100, volume_depth 1, direct integrator, sun + HDRI environment: 132.7 M samples per step.  `--config 1|3|4|5`
+selects the other BASELINE configurations (measurement table of BASELINE.md; see WORKLOADS below).
+  * ours      : vpt_render_passes(spp) through the C ABI (libvpt_b200.so).  N > 1 shards the frame by interleaved row
+                stripes over N ranks (scene replicated) and gathers the rank-local accumulators with NCCL.
+  * reference : the reference's own `volume_rt_kernel` (oracle/_ref, compiled from /root/reference), launched as
+                source/main.cpp:1823-1829 does: one launch + cudaDeviceSynchronize per spp, on the REFERENCE's own octree.
                 The reference has no CPU path and no multi-GPU path: rank 0 runs it on one GPU.
-Rank 0 prints ONE JSON line.  Timing: CUDA events on the launching stream around each step, L2 flushed
-between steps (excluded), barrier + synchronize on both sides, max over ranks.
+Rank 0 prints ONE JSON line.  Timing: CUDA events on the launching stream around each step, L2 flushed between steps
+(untimed), barrier + synchronize on both sides, max over ranks.  After the timed region (untimed) the frame of the timed
+configuration is rendered once more from a fresh state and compared with the reference kernel's frame ("parity"); with
+N > 1 rank 0 also checks that the gathered frame equals its own single-GPU frame bit for bit.  A parity failure exits non-zero.
 """
 import argparse
 import json
@@ -28,18 +31,61 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import torch
 
-WIDTH, HEIGHT, SPP = 1920, 1080, 64
 METRIC = "Msamples/sec (pixels x spp) on dragon.vdb 1920x1080"
+RTOL, ATOL, MAX_FLIPPED = 1e-4, 1e-5, 1e-3        # the parity tolerance of tests/test_parity_gpu.py
 
 
-def workload_params(V):
+# ---------------------------------------------------------------------------------------------------------------------
+# workloads: BASELINE.json configs, made concrete in SURVEY.md 8(d)
+# ---------------------------------------------------------------------------------------------------------------------
+def _kp(V, **over):
     kp = V.default_kernel_params()
-    kp.environment_type = 1          # HDRI environment
-    kp.ray_depth = 100
-    kp.volume_depth = 1
-    kp.integrator = 0
-    kp.max_interactions = 1000
+    kp.environment_type = 1; kp.max_interactions = 100000
+    for k, v in over.items(): setattr(kp, k, v)
     return kp
+
+
+def build_workload(V, cfg, dev):
+    """-> dict(name, scene, kp, width, height, spp, data, ref_ok)"""
+    hdri = "Barce_Rooftop_C_3k.hdr"
+    if cfg in (1, 2):
+        vol = V.Volume.load_vdb(V.find_asset("dragon.vdb"))
+        scene = V.Scene([vol.instance()], device=dev, env=hdri)
+        if cfg == 1:
+            return dict(name="dragon.vdb 512x512 1spp ray_depth=1 single scatter, sun + HDRI env (BASELINE configs[0]; the survey's environment_type 0 "
+                             "needs the Bruneton tables, see --config 1 note in BASELINE.md)", scene=scene, kp=_kp(V, ray_depth=1, volume_depth=1),
+                        width=512, height=512, spp=1, data="dragon.vdb (reference asset)", keep=[vol])
+        return dict(name="dragon.vdb 1920x1080 64spp ray_depth=100 volume_depth=1 direct integrator, sun + HDRI env (BASELINE configs[1])",
+                    scene=scene, kp=_kp(V, ray_depth=100, volume_depth=1, integrator=0), width=1920, height=1080, spp=64,
+                    data="dragon.vdb (reference asset)", keep=[vol])
+    if cfg == 3:
+        p = V.find_asset("fireball.vdb")
+        if p is None: raise SystemExit("fireball.vdb is not staged (oracle/_ref/assets)")
+        vol = V.Volume.load_vdb(p)
+        scene = V.Scene([vol.instance()], device=dev, env=hdri)
+        return dict(name="fireball.vdb 1920x1080 256spp emission + multiple scatter (ray_depth=2, volume_depth=50), sun + HDRI env (BASELINE configs[2])",
+                    scene=scene, kp=_kp(V, ray_depth=2, volume_depth=50, emission_scale=1.0, emission_pivot=1.0), width=1920, height=1080, spp=256,
+                    data="fireball.vdb density + heat (reference asset)", keep=[vol])
+    if cfg == 5:
+        vol = V.Volume.load_vdb(V.find_asset("dragon.vdb"))
+        n = int(os.environ.get("VPT_BENCH_INSTANCES", "1000"))
+        # fixed LCG: positions uniform in a cube, random unit quaternions, scale 1 (SURVEY 8(d) cfg 5)
+        state = 12345
+        def lcg():
+            nonlocal state
+            state = (1103515245 * state + 12345) & 0x7fffffff
+            return state / float(0x7fffffff)
+        inst = []
+        side = 6.0 * n ** (1.0 / 3.0)
+        for _ in range(n):
+            pos = tuple((lcg() - 0.5) * side for _ in range(3))
+            q = np.array([lcg() - 0.5 for _ in range(4)]); q /= max(np.linalg.norm(q), 1e-6)
+            inst.append(vol.instance(pos=pos, quat=tuple(q), scale=1.0))
+        scene = V.Scene(inst, device=dev, env=hdri)
+        return dict(name=f"{n} x dragon.vdb instances (LCG placement), 1920x1080 64spp ray_depth=50, sun + HDRI env (BASELINE configs[4])",
+                    scene=scene, kp=_kp(V, ray_depth=50, volume_depth=1), width=1920, height=1080, spp=64,
+                    data=f"dragon.vdb x {n} instances", keep=[vol], ref_max_instances=600)
+    raise SystemExit(f"--config {cfg} is not available in this build")
 
 
 class ClockSampler:
@@ -122,24 +168,34 @@ def timed_steps(step_fn, steps, warmup, dist, flush_buf, sampler=None):
     return ms, wall
 
 
-def cpu_baseline_sample(V, scene_args, cam, kp, seconds_target=12.0):
-    """CPU restatement (oracle/vpt_oracle.c, 'port') timed on the host cores over a bounded tile of the same workload."""
+def cpu_baseline_sample(V, scene, cam, kp, width, height, seconds_target=12.0):
+    """CPU restatement (oracle/vpt_oracle.c, 'port') timed on the host cores over a bounded sample of the same workload."""
     try:
         import oracle_cpu
     except Exception as e:                                     # pragma: no cover
         return {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
-    return oracle_cpu.timed_sample(scene_args, cam, kp, WIDTH, HEIGHT, seconds_target)
+    return oracle_cpu.timed_sample(scene, cam, kp, width, height, seconds_target)
+
+
+def frame_parity(got, want):
+    got = np.asarray(got, dtype=np.float64); want = np.asarray(want, dtype=np.float64)
+    d = np.abs(got - want)
+    bad = (d > ATOL + RTOL * np.abs(want)).reshape(-1, 3).any(axis=1)
+    return {"flipped_frac": float(bad.mean()), "max_abs": float(d.max()), "pixels": int(bad.size),
+            "tolerance": f"|d| <= {ATOL} + {RTOL}*|ref| per channel; flipped_frac must stay <= {MAX_FLIPPED}"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json configuration (1-based); 2 is the one the metric is quoted on")
     ap.add_argument("--chunk", type=int, default=0, help="passes fused per kernel round (0 = library default)")
     ap.add_argument("--sched-min-lanes", type=int, default=0, help="trace scheduler threshold (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) check of the timed frame against the reference kernel")
     ap.add_argument("--generic-kernel", action="store_true", help="A/B: force the generic trace kernel instantiation")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -159,20 +215,29 @@ def main():
 
     import vpt_b200 as V
     dev = f"cuda:{local if world > 1 else 0}"
-    vol = V.Volume.load_vdb(V.find_asset("dragon.vdb"))
-    scene = V.Scene([vol.instance()], device=dev, env="Barce_Rooftop_C_3k.hdr")
-    data = "dragon.vdb (reference asset) + " + ("Barce_Rooftop_C_3k.hdr" if not scene.data_notes else "; ".join(scene.data_notes))
-    kp = workload_params(V)
+    wl = build_workload(V, args.config, dev)
+    scene, kp, WIDTH, HEIGHT, SPP = wl["scene"], wl["kp"], wl["width"], wl["height"], wl["spp"]
+    data = wl["data"] + " + " + ("Barce_Rooftop_C_3k.hdr" if not scene.data_notes else "; ".join(scene.data_notes))
     flush_buf = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)
     samples_per_step = WIDTH * HEIGHT * SPP
     sampler = ClockSampler(local if world > 1 else 0)
-    config = {"workload": "dragon.vdb 1920x1080 64spp ray_depth=100 volume_depth=1 direct integrator, sun + HDRI env (BASELINE configs[1])",
-              "width": WIDTH, "height": HEIGHT, "spp_per_step": SPP, "l2": "flushed between steps (256 MiB rewrite, untimed)"}
+    config = {"workload": wl["name"], "baseline_config": args.config, "width": WIDTH, "height": HEIGHT, "spp_per_step": SPP,
+              "l2": "flushed between steps (256 MiB rewrite, untimed)"}
+    n_inst = len(scene.instances)
 
     if args.impl == "reference":
         import oracle_ref
+        if not oracle_ref.available():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (the reference kernel build) is not in this snapshot"}), flush=True)
+            return 0
+        if n_inst > wl.get("ref_max_instances", 10 ** 9):
+            # the reference overflows OCTNode::vol_indices[600] beyond 600 instances (quirk Q11): run it on the first 600
+            n_inst = wl["ref_max_instances"]
+            scene = V.Scene(scene.instances[:n_inst], device=dev, env="Barce_Rooftop_C_3k.hdr")
+            config["reference_instances"] = n_inst
         orc = oracle_ref.RefOracle(); orc.load_kernels()
         r = V.Renderer(scene, WIDTH, HEIGHT, kp=kp)
+        r.params.p_oct.value = orc.build_octree(scene.h_volumes, n_inst)      # the reference's own octree builder
         def step():
             r.kp.iteration = 0
             for _ in range(SPP):                               # main.cpp:1823-1829: launch, ++iteration, cudaDeviceSynchronize
@@ -183,7 +248,8 @@ def main():
         clocks = sampler.stop()
         val = samples_per_step * args.steps / (ms * 1e-3) / 1e6
         config.update({"launch_protocol": "reference main loop: 1 launch + cudaDeviceSynchronize per spp, grid (W/16+1,H/16+1)x(16,16)",
-                       "kernel": "source/render_kernel.cu compiled unmodified with -O3 --use_fast_math --maxrregcount=128 for sm_100a"})
+                       "kernel": "source/render_kernel.cu compiled unmodified with -O3 --use_fast_math --maxrregcount=128 for sm_100a",
+                       "octree": "reference build_octree (bvh_kernels.cu:582-604)"})
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": data, "config": config, "clocks": clocks, "gpu_launches": SPP * args.steps,
@@ -205,10 +271,9 @@ def main():
         r = dr.r
         def step():
             r.kp.iteration = 0
-            r.render(SPP, stream=stream)
-            dist.all_gather_into_tensor(dr.gathered, r.buffers.accum)
-            dr.full = dr.full_accum()
+            dr.render(SPP, stream=stream)
     else:
+        dr = None
         r = V.Renderer(scene, WIDTH, HEIGHT, kp=kp, options=opts)
         def step():
             r.kp.iteration = 0
@@ -229,16 +294,52 @@ def main():
     def step_e2e():
         step()
         if world > 1:
-            if rank == 0: pin_accum.copy_(dr.full.view(-1, 3), non_blocking=True)
+            if rank == 0: pin_accum.copy_(dr.full_accum().view(-1, 3), non_blocking=True)
         else:
             pin_accum.copy_(r.buffers.accum, non_blocking=True)
             pin_disp.copy_(r.buffers.display, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    ms_e2e, _ = timed_steps(step_e2e, max(3, args.steps // 2), 1, dist, flush_buf)
     e2e_steps = max(3, args.steps // 2)
+    ms_e2e, _ = timed_steps(step_e2e, e2e_steps, 1, dist, flush_buf)
     e2e_val = samples_per_step * e2e_steps / (ms_e2e * 1e-3) / 1e6
     h2d = 104 + 16 + 5 * 8 + 464 + 312                     # the by-value launch parameter block, per render call
     d2h = WIDTH * HEIGHT * (12 + 4) if world == 1 else (WIDTH * HEIGHT * 12 if rank == 0 else 0)
+
+    # ---- parity of the timed configuration (untimed): fresh state, same 64-spp frame, against the reference kernel ------------
+    parity = None
+    parity_fail = False
+    if not args.no_parity:
+        scene.reset_blue_noise(); r.kp.iteration = 0; r.buffers.zero_()
+        if world > 1:
+            dr.render(SPP, stream=stream); full = dr.full_accum().reshape(-1, 3).clone()
+        else:
+            r.render(SPP, stream=stream); full = r.buffers.accum
+        torch.cuda.synchronize()
+        if rank == 0:
+            parity = {}
+            if world > 1:
+                scene.reset_blue_noise()
+                one = V.Renderer(scene, WIDTH, HEIGHT, kp=_copy_kp(V, kp), cam=r.cam, options=opts)
+                one.render(SPP, stream=stream); torch.cuda.synchronize()
+                parity["gathered_equals_single_gpu_bitwise"] = bool(torch.equal(full, one.buffers.accum))
+                parity_fail |= not parity["gathered_equals_single_gpu_bitwise"]
+                one.close()
+            try:
+                import oracle_ref
+                have_ref = oracle_ref.available() and n_inst <= 600
+            except Exception:
+                have_ref = False
+            if have_ref:
+                orc = oracle_ref.RefOracle()
+                ref = V.Renderer(scene, WIDTH, HEIGHT, kp=_copy_kp(V, kp), cam=r.cam)
+                ref.params.p_oct.value = orc.build_octree(scene.h_volumes, n_inst)
+                scene.reset_blue_noise(); orc.render(ref, SPP)                 # race-free protocol
+                parity.update(frame_parity(full.cpu().numpy(), ref.buffers.accum.cpu().numpy()))
+                parity["against"] = "reference volume_rt_kernel (oracle/_ref), same parameter block, its own octree, same frame as timed"
+                parity_fail |= parity["flipped_frac"] > MAX_FLIPPED
+            else:
+                parity["against"] = "unavailable (oracle/_ref not in this snapshot, or > 600 instances: beyond the reference's capacity)"
+        if world > 1: dist.barrier()
 
     # ---- roofline of the dominant kernel (k_trace), measured live with CUDA events on its stream
     roofline = None
@@ -255,7 +356,7 @@ def main():
         for _ in range(2): render_only()
         torch.cuda.synchronize()
         kt = r.kernel_times()
-        r.set_option("profile", 0); r.set_option("count_stats", 1); r.counters(reset=True)   # work counters: generic instantiation, same algorithm
+        r.set_option("profile", 0); r.set_option("count_stats", 1); r.counters(reset=True)   # work counters of the SAME instantiation that was timed
         for _ in range(2): render_only()
         torch.cuda.synchronize()
         cnt = r.counters()
@@ -271,10 +372,13 @@ def main():
         achieved = bytes_trace / launches / (t_trace * 1e-3) / 1e9
         simt = cnt["lane_steps"] / max(1, 32 * cnt["warp_step_iters"])
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            if tj.get("passes_per_launch") == opts.get("passes_per_chunk", 32) and world == 1: traffic = tj["k_trace_dram_bytes_per_launch"]
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                if tj.get("passes_per_launch") == opts.get("passes_per_chunk", 32) and world == 1 and args.config == tj.get("baseline_config", 2):
+                    traffic = tj["k_trace_dram_bytes_per_launch"]
+                break
         bytes_per_sample = 88.0 + 32.0 * lookups_per_sample          # framebuffer stream + 32 B per density lookup
         step_gbs = value * bytes_per_sample / 1e3
         roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -283,27 +387,33 @@ def main():
                     "density_lookups_per_sample": lookups_per_sample, "rays_traced_per_sample": cnt["rays"] / max(1, samples),
                     "step_loop_simt_efficiency": simt, "service_round_lanes": cnt["lane_services"] / max(1, cnt["warp_service_rounds"]),
                     "kernel_ms_per_step": {k: v["ms"] / n_steps_prof for k, v in kt.items()},
-                    "step": {"bytes_per_sample": bytes_per_sample, "achieved": step_gbs, "frac": step_gbs / peak,
-                             "note": "whole step charged with SURVEY 8(d)'s 88 B + 32 B x lookups per sample"},
+                    "step": {"bytes_per_sample": bytes_per_sample, "achieved": step_gbs, "achieved_per_gpu": step_gbs / world, "frac": step_gbs / world / peak,
+                             "note": "whole step charged with SURVEY 8(d)'s 88 B + 32 B x lookups per sample; per-GPU rate over one GPU's peak"},
                     "note": "dragon.vdb is 425 KB: volume lookups are served by L1/TEX/L2, DRAM only sees the ray queue and the sample planes; "
                             "the path is bound by latency / instruction issue, not HBM (SURVEY 8(d)); see profiles/"}
 
     cpu_base = None
-    if rank == 0 and not args.no_cpu_baseline:
-        cpu_base = cpu_baseline_sample(V, scene, r.cam, kp)
+    if rank == 0 and not args.no_cpu_baseline and args.config in (1, 2):
+        cpu_base = cpu_baseline_sample(V, scene, r.cam, kp, WIDTH, HEIGHT)
 
     if rank == 0:
         config.update({"passes_per_chunk": opts.get("passes_per_chunk", 32), "partition": f"{world} rank(s), interleaved 8-row stripes" if world > 1 else "single GPU",
-                       "collective": "1 NCCL all_gather_into_tensor of float3 accumulators per step" if world > 1 else "none"})
+                       "collective": dr.collective_note if world > 1 else "none", "instances": n_inst})
         line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": data, "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu_base, "wall_s": wall}
+                "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu_base, "parity": parity, "wall_s": wall}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
-    return 0
+    return 1 if parity_fail else 0
+
+
+def _copy_kp(V, kp):
+    import ctypes as C
+    k = V.Kernel_params(); C.memmove(C.byref(k), C.byref(kp), C.sizeof(k)); k.iteration = 0
+    return k
 
 
 if __name__ == "__main__":

@@ -44,7 +44,9 @@ const char* vpt_version(void);
  * AtmosphereParameters, Kernel_params, point_light, VDB_INFO, AABB.  Returns how many entries exist. No CUDA call. */
 int  vpt_abi_sizes(size_t* out, int n);
 
-/* Tunables: "passes_per_chunk" (1..64, passes fused per generate/trace/resolve round, default 32),
+/* Tunables: "passes_per_chunk" (1..64 passes fused per generate/trace/resolve round; 0 = automatic, the default: 32, or 64 when the
+ * local frame has at most 2^20 pixels), "max_scratch_mb" (cap of the per-round ray queue + sample planes, default 12288),
+ * "gather_async" (see vpt_comm_*),
  * "sched_min_lanes" (1..32, lanes an operation must gather in a warp before it pre-empts stepping, default 20),
  * "ctas_per_sm" (0 = occupancy maximum), "count_stats" / "profile" (0|1, see vpt_get_counters / vpt_get_kernel_times). */
 int  vpt_set_option(vpt_context* ctx, const char* key, int value);
@@ -59,6 +61,23 @@ long long vpt_local_pixels(const vpt_context* ctx, unsigned width, unsigned heig
  * scatter them back into a full row-major frame. */
 int  vpt_unpermute(vpt_context* ctx, const void* d_gathered, void* d_full, unsigned width, unsigned height,
                    int elem_bytes, void* stream);
+
+/* Multi-GPU exchange, issued by the library itself (one process per GPU, NCCL).  One rank obtains an id
+ * (ncclGetUniqueId) and hands the 128 bytes to every rank by whatever means the application has (MPI, torch.distributed,
+ * a file); every rank then calls vpt_comm_init (collective: ncclCommInitRank; also applies vpt_set_partition).  With a
+ * gather target set, every vpt_render_pass(es) call ends with ONE ncclAllGather of the rank-local accumulators (and one of
+ * the display words if asked) + the stripe un-permutation into the caller's full-frame buffers -- row-major [H][W] float3 /
+ * uint32, allocated by the caller on every rank -- enqueued on the caller's stream behind the last kernel.  Option
+ * "gather_async" = 1 moves that exchange to a side stream so the next call's sampling kernels overlap it; the library waits
+ * for it before the next call overwrites the accumulator, and vpt_comm_wait(ctx, stream) makes `stream` wait for it.
+ * NCCL is bound at run time (dlopen): without it these entry points fail with VPT_ERR_UNSUPPORTED, everything else works. */
+#define VPT_COMM_ID_BYTES 128
+int  vpt_comm_get_unique_id(unsigned char id_out[VPT_COMM_ID_BYTES]);
+int  vpt_comm_init(vpt_context* ctx, const unsigned char id[VPT_COMM_ID_BYTES], int rank, int n_ranks, int stripe_rows);
+int  vpt_comm_set_gather(vpt_context* ctx, void* d_full_accum_f3, void* d_full_display_u32);   /* either may be NULL */
+int  vpt_comm_wait(vpt_context* ctx, void* stream);
+int  vpt_comm_info(vpt_context* ctx, int* nccl_version, int* rank, int* n_ranks);
+int  vpt_comm_destroy(vpt_context* ctx);
 
 /* ---- the hot path --------------------------------------------------------------------------------
  * vpt_render_pass   replaces ONE launch of the reference `volume_rt_kernel` (render_kernel.cu:2216):
@@ -102,10 +121,15 @@ int  vpt_texture_create_env(const float* host_rgba, unsigned width, unsigned hei
  * main.cpp:647-867): from a res x res table of the sky's luminous power over (azimuth = x, elevation = y) builds the
  * row-conditional cdf, the marginal function and its cdf, and wraps all four as point-sampled unnormalised float
  * textures (2-D, 2-D, 1-D, 1-D).  tex_out / arrays_out order: env_func_tex, env_cdf_tex, env_marginal_func_tex,
- * env_marginal_cdf_tex; *marginal_int_out is Kernel_params.env_marginal_int; env_sample_tex_res = res.  The reference's
- * version reads/writes one element outside its arrays at the row starts (cdf_p - 1, marginal_cdf_p - 1); this one
- * uses 0 for those out-of-range reads. */
+ * env_marginal_cdf_tex; *marginal_int_out is Kernel_params.env_marginal_int; env_sample_tex_res = res.  The arithmetic is
+ * vpt_env_tables_compute's. */
 int  vpt_env_tables_create(const float* func, unsigned res, vpt_tex_t tex_out[4], void* arrays_out[4], float* marginal_int_out);
+/* The host arithmetic of create_cdf (main.cpp:681-757) on caller-provided arrays (cdf: res*res, marginal_func / marginal_cdf:
+ * res), literally: row y > 0 of the conditional cdf starts from func[y-1][res-1] / res (the reference's `*(func_p - 1)` at x == 0
+ * is the previous row's last element), the uniform fallback is selected by marginal_func[0] == 0, the last cdf entry of each
+ * row is 1.  The only two reads the reference makes OUTSIDE its arrays (func[-1], marginal_cdf[-1]; quirk Q20) are taken as 0.
+ * Pure host code, no device needed. */
+int  vpt_env_tables_compute(const float* func, unsigned res, float* cdf, float* marginal_func, float* marginal_cdf, float* marginal_int_out);
 /* The table create_cdf feeds into the above: luminous power of the reference's HOST-side analytic sky (single-scattering
  * Rayleigh + Mie march, 16 x 8 samples, main.cpp:242-301) over res x res directions, func[y*res + x] =
  * |sky(dir(az = x/(res-1)*2pi, el = y/(res-1)*pi)) * sky_color| (main.cpp:683-693; the reference uses res = 180 and

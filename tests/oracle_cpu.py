@@ -126,6 +126,11 @@ def timed_sample(scene, cam, kp, width, height, seconds_target=12.0):
     k = V.Kernel_params(); C.memmove(C.byref(k), C.byref(kp), C.sizeof(k)); k.iteration = 0
     k.resolution = V.u2(width, height)
     cores = os.cpu_count() or 1
+    try:                                    # torchrun exports OMP_NUM_THREADS=1: ask the OpenMP runtime for all host cores and report what it grants
+        gomp = C.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(int(cores)); cores = int(gomp.omp_get_max_threads())
+    except OSError:
+        cores = int(os.environ.get("OMP_NUM_THREADS", cores))
     # the whole frame, as many passes as fit the time target (64 at most: the workload's own count)
     tw, th, spp = 1920, 1080, 1
     rect = ((width - tw) // 2, (height - th) // 2, (width + tw) // 2, (height + th) // 2)

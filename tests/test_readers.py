@@ -230,3 +230,41 @@ def test_corrupt_image_files_fail_cleanly(tmp_path):
             except V.VptError:
                 bad += 1
         assert bad > 20, name
+
+
+_CDF_REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libcreate_cdf_ref.so")
+
+
+@pytest.mark.skipif(not os.path.exists(_CDF_REF), reason="oracle/_ref/libcreate_cdf_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("kind", ["sky", "random", "zero_first_row", "all_zero", "spiky"])
+def test_env_tables_equal_the_reference_create_cdf_bit_for_bit(kind):
+    """VERDICT r1 item 6 / ADVICE: the env sampling tables against the reference's OWN create_cdf arithmetic (main.cpp:681-751,
+    compiled from /root/reference into oracle/_ref; its two out-of-array reads see 0).  Bit-exact, including the carry-over of the
+    previous row's last element into every row y > 0 and the marginal_func[0] == 0 fallback rule."""
+    import ctypes as C
+    from vpt_b200.scene import sky_power_table
+    res = 180
+    rng = np.random.RandomState(4)
+    if kind == "sky": func = sky_power_table(120.0, 30.0, (1.0, 0.9, 0.8), res)
+    elif kind == "random": func = rng.rand(res, res).astype(np.float32) * 3.0
+    elif kind == "zero_first_row": func = rng.rand(res, res).astype(np.float32); func[0, :] = 0.0
+    elif kind == "all_zero": func = np.zeros((res, res), dtype=np.float32)
+    else: func = np.maximum((rng.rand(res, res) ** 8).astype(np.float32) * 100.0, np.float32(1e-12)); func[50, :] = 0.0   # (no underflow in the stand-in's sqrt(v*v))
+    func = np.ascontiguousarray(func, dtype=np.float32)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    ref = C.CDLL(_CDF_REF)
+    ref.vptref_create_cdf.argtypes = [C.POINTER(C.c_float)] * 5 + [C.POINTER(C.c_float), C.c_float]
+    r_func = np.empty((res, res), np.float32); r_cdf = np.empty((res, res), np.float32)
+    r_mf = np.empty(res, np.float32); r_mc = np.empty(res, np.float32); r_int = C.c_float(0)
+    assert ref.vptref_create_cdf(fp(func), fp(r_func), fp(r_cdf), fp(r_mf), fp(r_mc), C.byref(r_int), 0.0) == 0
+    assert np.array_equal(r_func, func)                                     # the stand-in sky reproduced the table exactly
+    cdf = np.empty((res, res), np.float32); mf = np.empty(res, np.float32); mc = np.empty(res, np.float32); mint = C.c_float(0)
+    assert V.lib.vpt_env_tables_compute(fp(func), res, fp(cdf), fp(mf), fp(mc), C.byref(mint)) == 0
+    same = lambda a, b: np.array_equal(a.view(np.uint32), b.view(np.uint32)) or np.array_equal(a, b, equal_nan=True)
+    assert same(mf, r_mf), "marginal_func"
+    assert same(cdf, r_cdf), "conditional cdf"
+    assert same(mc, r_mc), "marginal cdf"
+    assert np.float32(mint.value) == np.float32(r_int.value) or (np.isnan(mint.value) and np.isnan(r_int.value))
+    if kind in ("sky", "random"):
+        assert np.all(cdf[:, -1] == 1.0) and np.all(np.diff(mc) >= 0) and abs(mc[-1] - 1.0) < 1e-5
+        assert np.allclose(cdf[1:, 0] * mf[1:], func[:-1, -1] / res, rtol=1e-5)   # the carry-over is really there

@@ -152,7 +152,8 @@ EXPORTED_SYMBOLS = [
     "vpt_bmp_load_rbg", "vpt_exr_load_rgb", "vpt_free", "vpt_octree_build", "vpt_octree_destroy", "vpt_volume_bounds",
     "vpt_camera_look_at", "vpt_kernel_params_defaults", "vpt_get_counters", "vpt_get_kernel_times", "vpt_octree_read",
     "vpt_env_tables_create", "vpt_ins_load", "vpt_env_sky_tabulate",
-    "vpt_octree_info", "vpt_octree_read_flat", "vpt_bvh_build", "vpt_bvh_read", "vpt_bvh_destroy",
+    "vpt_octree_info", "vpt_octree_read_flat", "vpt_bvh_build", "vpt_bvh_read", "vpt_bvh_destroy", "vpt_env_tables_compute",
+    "vpt_comm_get_unique_id", "vpt_comm_init", "vpt_comm_set_gather", "vpt_comm_wait", "vpt_comm_info", "vpt_comm_destroy",
 ]
 
 # ---- prototypes ------------------------------------------------------------------------------------
@@ -179,6 +180,18 @@ lib.vpt_texture_create_env.restype = C.c_int
 lib.vpt_texture_destroy.argtypes = [C.c_uint64, _vp]; lib.vpt_texture_destroy.restype = C.c_int
 lib.vpt_env_tables_create.argtypes = [C.POINTER(C.c_float), C.c_uint, C.POINTER(C.c_uint64), C.POINTER(_vp), C.POINTER(C.c_float)]
 lib.vpt_env_tables_create.restype = C.c_int
+
+
+lib.vpt_env_tables_compute.argtypes = [C.POINTER(C.c_float), C.c_uint, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+lib.vpt_env_tables_compute.restype = C.c_int
+
+
+lib.vpt_comm_get_unique_id.argtypes = [C.POINTER(C.c_ubyte)]; lib.vpt_comm_get_unique_id.restype = C.c_int
+lib.vpt_comm_init.argtypes = [_vp, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int]; lib.vpt_comm_init.restype = C.c_int
+lib.vpt_comm_set_gather.argtypes = [_vp, _vp, _vp]; lib.vpt_comm_set_gather.restype = C.c_int
+lib.vpt_comm_wait.argtypes = [_vp, _vp]; lib.vpt_comm_wait.restype = C.c_int
+lib.vpt_comm_info.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]; lib.vpt_comm_info.restype = C.c_int
+lib.vpt_comm_destroy.argtypes = [_vp]; lib.vpt_comm_destroy.restype = C.c_int
 
 
 class ins_header(C.Structure):

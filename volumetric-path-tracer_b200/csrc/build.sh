@@ -16,5 +16,6 @@ g++ -O2 -std=c++17 -fPIC -c "$HERE/host/vdb_reader.cpp" -o "$HERE/_obj/vdb_reade
 g++ -O2 -std=c++17 -fPIC -c "$HERE/host/image_io.cpp" -o "$HERE/_obj/image_io.o"
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -c "$HERE/host/sky_table.cpp" -o "$HERE/_obj/sky_table.o"
 LIBNAME="${VPT_LIB_NAME:-libvpt_b200.so}"
-$NVCC $ARCH -shared -o "$OUT/$LIBNAME" "$HERE"/_obj/*.o -lz
+$NVCC $ARCH -O2 -std=c++17 -Xcompiler -fPIC -x cu -c "$HERE/host/vpt_comm.cpp" -o "$HERE/_obj/vpt_comm.o"
+$NVCC $ARCH -shared -o "$OUT/$LIBNAME" "$HERE"/_obj/*.o -lz -ldl
 echo "built $OUT/$LIBNAME"

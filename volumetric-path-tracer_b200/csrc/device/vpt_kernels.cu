@@ -236,22 +236,38 @@ k_generate(const FrameArgs fa)
         const float u = __fdividef(padd((float)x, bnx), (float)kp.resolution.x);
         const float v = __fdividef(padd((float)y, bny), (float)kp.resolution.y);
 
-        // thin-lens ray (reference camera::get_ray, camera.h:131-136)
-        float3 p;
-        do {
-            const float a = vdc2[int(rng.next() * 100)];
-            const float b = vdc3[int(rng.next() * 100)];
-            p = f3(pfma(a, 2.0f, -1.0f), pfma(b, 2.0f, -1.0f), 0.0f);
-        } while (pfma(p.x, p.x, pmul(p.y, p.y)) >= 1.0f);
-        const float3 rd = f3(pmul(cam.lens_radius, p.x), pmul(cam.lens_radius, p.y), 0.0f);
-        const float3 offset = f3(pfma(cam.u.x, rd.x, pmul(cam.v.x, rd.y)), pfma(cam.u.y, rd.x, pmul(cam.v.y, rd.y)), pfma(cam.u.z, rd.x, pmul(cam.v.z, rd.y)));
-        (void)rng.next();                                        // shutter time draw (value unused by the path)
-        org = f3(padd(cam.origin.x, offset.x), padd(cam.origin.y, offset.y), padd(cam.origin.z, offset.z));
-        const float3 b = f3(psub(psub(pfma(cam.vertical.x, v, pfma(cam.horizontal.x, u, cam.lower_left_corner.x)), cam.origin.x), offset.x),
-                            psub(psub(pfma(cam.vertical.y, v, pfma(cam.horizontal.y, u, cam.lower_left_corner.y)), cam.origin.y), offset.y),
-                            psub(psub(pfma(cam.vertical.z, v, pfma(cam.horizontal.z, u, cam.lower_left_corner.z)), cam.origin.z), offset.z));
-        dir = normalize(b);
-        kdraws = rng.k;
+        // thin-lens ray (reference camera::get_ray, camera.h:131-136).  The lens sample is drawn by a rejection loop on the pixel's
+        // Philox stream BEFORE the ray exists -- but with a pinhole (lens_radius == 0) the sample is multiplied by zero: the ray
+        // does not depend on it and the only thing the path needs from the loop is HOW MANY draws it consumed.  So the pinhole ray is
+        // built first, the box / octree prefix below decides whether the sample can hit anything, and only the survivors run the
+        // generator (70 % of the samples of the headline frame are misses and never touch it).  Bit-exactness: offset = u*0*p.x +
+        // v*0*p.y is +-0; x + (+-0) == x and x - (+-0) == x for every x != 0, so lanes where a zero could meet a signed zero
+        // (an origin or direction component that is exactly 0) take the literal order instead.
+        const bool pinhole = (cam.lens_radius == 0.0f) && cam.origin.x != 0.0f && cam.origin.y != 0.0f && cam.origin.z != 0.0f;
+        bool lens_pending = false;
+        {
+            const float3 b0 = f3(psub(pfma(cam.vertical.x, v, pfma(cam.horizontal.x, u, cam.lower_left_corner.x)), cam.origin.x),
+                                 psub(pfma(cam.vertical.y, v, pfma(cam.horizontal.y, u, cam.lower_left_corner.y)), cam.origin.y),
+                                 psub(pfma(cam.vertical.z, v, pfma(cam.horizontal.z, u, cam.lower_left_corner.z)), cam.origin.z));
+            if (pinhole && b0.x != 0.0f && b0.y != 0.0f && b0.z != 0.0f) {
+                org = ld3(cam.origin);
+                dir = normalize(b0);
+                lens_pending = true;
+            } else {
+                float3 p;
+                do {
+                    const float a = vdc2[int(rng.next() * 100)];
+                    const float b = vdc3[int(rng.next() * 100)];
+                    p = f3(pfma(a, 2.0f, -1.0f), pfma(b, 2.0f, -1.0f), 0.0f);
+                } while (pfma(p.x, p.x, pmul(p.y, p.y)) >= 1.0f);
+                const float3 rd = f3(pmul(cam.lens_radius, p.x), pmul(cam.lens_radius, p.y), 0.0f);
+                const float3 offset = f3(pfma(cam.u.x, rd.x, pmul(cam.v.x, rd.y)), pfma(cam.u.y, rd.x, pmul(cam.v.y, rd.y)), pfma(cam.u.z, rd.x, pmul(cam.v.z, rd.y)));
+                ++rng.k;                                                 // shutter time draw: consumed, value unused by the path
+                org = f3(padd(cam.origin.x, offset.x), padd(cam.origin.y, offset.y), padd(cam.origin.z, offset.z));
+                dir = normalize(f3(psub(b0.x, offset.x), psub(b0.y, offset.y), psub(b0.z, offset.z)));
+                kdraws = rng.k;
+            }
+        }
 
         const bool sphere_clear = line_misses_sphere(sph, org, dir);   // then sphere::intersect is known to fail: skip it
         if (sphere_clear) { float tmax1; obj = aabb_intersect(sc.root_pmin, sc.root_pmax, org, dir, t_min, tmax1) ? 1 : 0; }
@@ -274,6 +290,16 @@ k_generate(const FrameArgs fa)
             }
             else if (leaf >= 0) { prestepped = true; wstart = p; }
             // leaf == -2 after 256 hops: leave it to the generic route
+        }
+
+        if (hit && lens_pending) {
+            // the rejection loop, for its draw count only (2 per trial + the shutter-time draw)
+            float px, py;
+            do {
+                px = pfma(vdc2[int(rng.next() * 100)], 2.0f, -1.0f);
+                py = pfma(vdc3[int(rng.next() * 100)], 2.0f, -1.0f);
+            } while (pfma(px, px, pmul(py, py)) >= 1.0f);
+            kdraws = rng.k + 1u;
         }
 
         if (!hit) {

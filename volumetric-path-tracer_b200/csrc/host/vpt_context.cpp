@@ -27,55 +27,18 @@
 static thread_local std::string g_last_error;
 namespace vpt { int fail_global(int code, const std::string& msg) { g_last_error = msg; return code; } }
 
-struct vpt_context {
-    int device = 0;
-    int num_sms = 0;
-    std::string err;
-    // options
-    int passes_per_chunk = 32;
-    int ctas_per_sm = 0;
-    // partition
-    int rank = 0, n_ranks = 1, stripe_rows = 16;
-    // scene cache: keyed by the two device pointers AND the registry generation of the octree (a rebuilt octree that got the
-    // same address back is a different scene); the cheap per-volume records are refreshed whenever a new frame starts
-    vpt_devptr_t cached_volumes = 0, cached_root = 0;
-    unsigned long long cached_generation = 0;
-    bool   scene_single_volume = false;
-    size_t cap_vrec = 0;              // VolumeRec capacity (grows with the instance count)
-    int*   h_pinned = nullptr;        // one pinned word for the 4-byte read-back a foreign octree needs
-    int    max_ctas[3] = {0, 0, 0};   // k_trace occupancy per instantiation: [0] generic, [1] lean, [2] volumetric path
-    int    force_generic = 0;        // option "generic_kernel": 1 = never use the lean trace instantiation (A/B and tests)
-    vpt::SceneTables* d_scene = nullptr;
-    vpt::OctInternal* d_internal = nullptr;
-    uint2* d_leaf_list = nullptr;
-    int* d_leaf_indices = nullptr;
-    vpt::VolumeRec* d_vrec = nullptr;
-    // frame buffers
-    size_t cap_samples = 0;           // n_local * chunk
-    bool   cap_planeD = false;
-    uint2* d_queue_id = nullptr; float4* d_queue_org = nullptr; float2* d_bn_table = nullptr; int cap_chunk = 0;
-    int sched_min_lanes = 20;
-    int debug_flags = 0;
-    float4 *d_queue = nullptr, *d_planeA = nullptr, *d_planeB = nullptr, *d_planeC = nullptr, *d_planeD = nullptr;
-    unsigned* d_counters = nullptr;   // [0] queue_count, [1] queue_head
-    // stats
-    unsigned long long launches = 0;
-    int count_stats = 0;              // option "count_stats": accumulate trace counters
-    unsigned long long* d_stats = nullptr;   // 8 counters
-    int profile = 0;                  // option "profile": CUDA-event timing of every kernel (debug / bench breakdown)
-    struct Ev { int kind; cudaEvent_t a, b; };
-    std::vector<Ev> events;
-};
-
 static int fail(vpt_context* ctx, int code, const std::string& msg) {
     g_last_error = msg;
     if (ctx) ctx->err = msg;
     return code;
 }
+namespace vpt { int fail_ctx(vpt_context* ctx, int code, const std::string& msg) { return fail(ctx, code, msg); } }
 #define VPT_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     return fail(ctx, VPT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
-static vpt::FrameGeom make_geom(const vpt_context* c, unsigned w, unsigned h) {
+namespace vpt { FrameGeom make_frame_geom(const vpt_context* c, unsigned w, unsigned h); }
+static vpt::FrameGeom make_geom(const vpt_context* c, unsigned w, unsigned h) { return vpt::make_frame_geom(c, w, h); }
+vpt::FrameGeom vpt::make_frame_geom(const vpt_context* c, unsigned w, unsigned h) {
     vpt::FrameGeom g;
     g.width = (int)w; g.height = (int)h; g.n_ranks = c->n_ranks; g.rank = c->rank;
     if (c->n_ranks == 1) { g.stripe_h = (int)h > 0 ? (int)h : 1; g.local_rows = (int)h; }
@@ -110,6 +73,7 @@ static void free_context(vpt_context* c) {
     cudaFree(c->d_scene); cudaFree(c->d_internal); cudaFree(c->d_leaf_list); cudaFree(c->d_leaf_indices); cudaFree(c->d_vrec);
     cudaFree(c->d_stats);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    vpt_comm_destroy(c);
     for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaFree(c->d_queue_id); cudaFree(c->d_queue_org); cudaFree(c->d_bn_table);
     cudaFree(c->d_counters); cudaFree(c->d_queue); cudaFree(c->d_planeA); cudaFree(c->d_planeB); cudaFree(c->d_planeC); cudaFree(c->d_planeD);
@@ -149,7 +113,9 @@ void vpt_destroy(vpt_context* c) { free_context(c); }
 int vpt_set_option(vpt_context* c, const char* key, int value) {
     if (!c || !key) return fail(c, VPT_ERR_INVALID, "vpt_set_option: null argument");
     const std::string k(key);
-    if (k == "passes_per_chunk") { if (value < 1 || value > 64) return fail(c, VPT_ERR_INVALID, "passes_per_chunk must be 1..64"); c->passes_per_chunk = value; }
+    if (k == "passes_per_chunk") { if (value < 0 || value > 64) return fail(c, VPT_ERR_INVALID, "passes_per_chunk must be 0 (automatic) or 1..64"); c->chunk_auto = value == 0; if (value) c->passes_per_chunk = value; }
+    else if (k == "max_scratch_mb") { if (value < 64) return fail(c, VPT_ERR_INVALID, "max_scratch_mb must be >= 64"); c->max_scratch_bytes = (size_t)value << 20; }
+    else if (k == "gather_async") { c->gather_async = value ? 1 : 0; }
     else if (k == "ctas_per_sm") { if (value < 0 || value > 8) return fail(c, VPT_ERR_INVALID, "ctas_per_sm must be 0..8"); c->ctas_per_sm = value; }
     else if (k == "sched_min_lanes") { if (value < 1 || value > 32) return fail(c, VPT_ERR_INVALID, "sched_min_lanes must be 1..32"); c->sched_min_lanes = value; }
     else if (k == "debug_flags") { c->debug_flags = value; }
@@ -310,8 +276,17 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         n_sampled = n_passes < left ? n_passes : left;
     }
 
-    const int chunk = c->passes_per_chunk;
+    // passes fused per generate/trace/resolve round: 32 by default; a small local frame (multi-GPU shard, low resolution)
+    // takes up to 64 so the fixed per-round cost and the persistent kernel's tail are paid half as often; always capped so
+    // the per-round scratch (ray queue + sample planes, 88 B or 104 B per sample) stays under max_scratch_bytes
     const bool planeD = sky_env;
+    int chunk = c->passes_per_chunk;
+    if (c->chunk_auto) chunk = (size_t)fa.geom.n_local <= ((size_t)1 << 20) ? 64 : 32;
+    {
+        const size_t per_sample = 88 + (planeD ? 16 : 0);
+        const size_t fit = c->max_scratch_bytes / (per_sample * (size_t)(fa.geom.n_local > 0 ? fa.geom.n_local : 1));
+        if ((size_t)chunk > fit) chunk = fit < 1 ? 1 : (int)fit;
+    }
     if (n_sampled) {
         const size_t per_chunk = (size_t)fa.geom.n_local * (size_t)(n_sampled < (unsigned)chunk ? n_sampled : (unsigned)chunk);
         int rc = ensure_frame_buffers(c, per_chunk, planeD);
@@ -352,6 +327,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         VPT_CUDA(c, timed(0, [&] { return vpt::launch_generate(fa, (int)np, stream); }));
         VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, vol_integ ? &atmo : nullptr, lean, trace_ctas, stream); }));
         const bool last = (done + np == n_passes);
+        if (c->gather_pending) { int rc = vpt::comm_before_accum_write(c, stream); if (rc != VPT_OK) return rc; }
         VPT_CUDA(c, timed(2, [&] { return vpt::launch_resolve(fa, sky, (int)np, 1, last ? 1 : 0, stream); }));
         c->launches += 4;
         done += np;
@@ -359,9 +335,15 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
     if (n_sampled < n_passes) {
         // passes that no longer sample: WHITE / re-tonemap semantics of the kernel tail
         fa.kp.iteration = it0 + n_sampled;
+        if (c->gather_pending) { int rc = vpt::comm_before_accum_write(c, stream); if (rc != VPT_OK) return rc; }
         VPT_CUDA(c, vpt::launch_resolve(fa, sky, (int)(n_passes - n_sampled), 0, 1, stream));
         VPT_CUDA(c, vpt::launch_bn_advance((void*)kp.blue_noise_buffer, (int)(n_passes - n_sampled), stream));
         c->launches += 2;
+    }
+    // multi-GPU: the one collective of the path -- all-gather of the rank-local frame into the caller's full-frame buffers
+    if (c->nccl_comm && (c->d_full_accum || c->d_full_display)) {
+        int rc = vpt::comm_gather_frame(c, fa.geom, (const void*)kp.accum_buffer, (const void*)kp.display_buffer, stream);
+        if (rc != VPT_OK) return rc;
     }
     return VPT_OK;
 }
@@ -456,30 +438,52 @@ static int create_table_texture(const float* data, unsigned w, unsigned h, vpt_t
     return VPT_OK;
 }
 
+// Host arithmetic of create_cdf (main.cpp:681-757), pointer walk restated with indices.  The reference reads one element
+// BEFORE two of its arrays (quirk Q20): `*(func_p - 1)` at y == 0, x == 0 and `*(marginal_cdf_p - 1)` at y == 0; those two reads
+// are taken as 0 here (in the reference they hit the allocator's bookkeeping word: a denormal).  Everything else is literal:
+//   * row y > 0 starts from func[y-1][res-1] / res, because `*(func_p - 1)` at x == 0 is the LAST element of the previous row
+//     (in range), and that offset is carried through the row's cdf and into marginal_func[y];
+//   * `*(cdf_p - 1) = 0` at each row start zeroes the previous row's last cdf entry, which the normalisation then sets to 1;
+//   * the "total" that selects the uniform fallback is res x marginal_func[0] (the loop never advances its pointer).
+int vpt_env_tables_compute(const float* func, unsigned res, float* cdf, float* marginal_func, float* marginal_cdf, float* marginal_int_out) {
+    if (!func || res < 2 || !cdf || !marginal_func || !marginal_cdf || !marginal_int_out) return fail(nullptr, VPT_ERR_INVALID, "vpt_env_tables_compute: bad arguments");
+    const float fres = (float)res;
+    for (unsigned y = 0; y < res; ++y) {
+        float prev_cdf = 0.0f;                                          // *(cdf_p - 1) = .0f
+        if (y > 0) cdf[(size_t)y * res - 1] = 0.0f;
+        for (unsigned x = 0; x < res; ++x) {
+            const float prev_func = (x == 0 && y == 0) ? 0.0f : func[(size_t)y * res + x - 1];
+            prev_cdf = prev_cdf + prev_func / fres;
+            cdf[(size_t)y * res + x] = prev_cdf;
+        }
+        marginal_func[y] = prev_cdf;
+    }
+    float total_int = 0.0f;
+    for (unsigned j = 0; j < res; ++j) total_int += marginal_func[0];
+    if (total_int == 0.0f) {
+        for (unsigned y = 0; y < res; ++y) for (unsigned x = 0; x < res; ++x) cdf[(size_t)y * res + x] = ((float)x / fres) * ((float)y / fres);
+    } else {
+        for (unsigned y = 0; y < res; ++y) for (unsigned x = 0; x < res; ++x) {
+            float& c = cdf[(size_t)y * res + x];
+            c /= marginal_func[y];
+            if (x == res - 1) c = 1.0f;
+        }
+    }
+    float run = 0.0f;                                                   // *(marginal_cdf_p - 1) at y == 0: out of range, taken as 0
+    for (unsigned y = 0; y < res; ++y) { run = run + marginal_func[y] / fres; marginal_cdf[y] = run; }
+    const float marginal_int = run;
+    if (marginal_int > 0.0f) for (unsigned y = 0; y < res; ++y) marginal_cdf[y] /= std::max(.000001f, marginal_int);
+    else marginal_cdf[0] = 1.0f;                                        // the reference's trailing `*marginal_cdf_p = 1.0f` lands here when the loop is skipped
+    *marginal_int_out = marginal_int;
+    return VPT_OK;
+}
+
 int vpt_env_tables_create(const float* func, unsigned res, vpt_tex_t tex_out[4], void* arrays_out[4], float* marginal_int_out) {
     if (!func || res < 2 || !tex_out || !arrays_out || !marginal_int_out) return fail(nullptr, VPT_ERR_INVALID, "vpt_env_tables_create: bad arguments");
     const size_t n = (size_t)res * res;
     std::vector<float> cdf(n), mfunc(res), mcdf(res);
-    float total = 0.f;
-    for (unsigned y = 0; y < res; ++y) {
-        float run = 0.f;
-        for (unsigned x = 0; x < res; ++x) {                       // cdf[x] = sum of func[0..x-1] / res
-            if (x) run += func[(size_t)y * res + x - 1] / (float)res;
-            cdf[(size_t)y * res + x] = run;
-        }
-        mfunc[y] = run; total += run;
-    }
-    for (unsigned y = 0; y < res; ++y)
-        for (unsigned x = 0; x < res; ++x) {
-            float& c = cdf[(size_t)y * res + x];
-            if (total == 0.f) c = ((float)x / (float)res) * ((float)y / (float)res);
-            else { c /= mfunc[y]; if (x == res - 1) c = 1.0f; }
-        }
-    float run = 0.f;
-    for (unsigned y = 0; y < res; ++y) { run += mfunc[y] / (float)res; mcdf[y] = run; }
-    const float marginal_int = run;
-    if (marginal_int > 0.f) for (unsigned y = 0; y < res; ++y) mcdf[y] /= std::max(.000001f, marginal_int);
-    *marginal_int_out = marginal_int;
+    int rc0 = vpt_env_tables_compute(func, res, cdf.data(), mfunc.data(), mcdf.data(), marginal_int_out);
+    if (rc0 != VPT_OK) return rc0;
     const float* src[4] = { func, cdf.data(), mfunc.data(), mcdf.data() };
     const unsigned heights[4] = { res, res, 0u, 0u };
     for (int i = 0; i < 4; ++i) { tex_out[i] = 0; arrays_out[i] = nullptr; }

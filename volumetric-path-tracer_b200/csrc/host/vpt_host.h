@@ -6,6 +6,60 @@
 #include <cuda_runtime.h>
 #include <string>
 
+#include <vector>
+
+struct vpt_context {
+    int device = 0;
+    int num_sms = 0;
+    std::string err;
+    // options
+    int passes_per_chunk = 32;
+    int ctas_per_sm = 0;
+    // partition
+    int rank = 0, n_ranks = 1, stripe_rows = 16;
+    // scene cache: keyed by the two device pointers AND the registry generation of the octree (a rebuilt octree that got the
+    // same address back is a different scene); the cheap per-volume records are refreshed whenever a new frame starts
+    vpt_devptr_t cached_volumes = 0, cached_root = 0;
+    unsigned long long cached_generation = 0;
+    bool   scene_single_volume = false;
+    size_t cap_vrec = 0;              // VolumeRec capacity (grows with the instance count)
+    int*   h_pinned = nullptr;        // one pinned word for the 4-byte read-back a foreign octree needs
+    int    max_ctas[3] = {0, 0, 0};   // k_trace occupancy per instantiation: [0] generic, [1] lean, [2] volumetric path
+    int    force_generic = 0;        // option "generic_kernel": 1 = never use the lean trace instantiation (A/B and tests)
+    vpt::SceneTables* d_scene = nullptr;
+    vpt::OctInternal* d_internal = nullptr;
+    uint2* d_leaf_list = nullptr;
+    int* d_leaf_indices = nullptr;
+    vpt::VolumeRec* d_vrec = nullptr;
+    // frame buffers
+    size_t cap_samples = 0;           // n_local * chunk
+    bool   cap_planeD = false;
+    uint2* d_queue_id = nullptr; float4* d_queue_org = nullptr; float2* d_bn_table = nullptr; int cap_chunk = 0;
+    int sched_min_lanes = 20;
+    int debug_flags = 0;
+    float4 *d_queue = nullptr, *d_planeA = nullptr, *d_planeB = nullptr, *d_planeC = nullptr, *d_planeD = nullptr;
+    unsigned* d_counters = nullptr;   // [0] queue_count, [1] queue_head
+    // stats
+    unsigned long long launches = 0;
+    int count_stats = 0;              // option "count_stats": accumulate trace counters
+    unsigned long long* d_stats = nullptr;   // 8 counters
+    int profile = 0;                  // option "profile": CUDA-event timing of every kernel (debug / bench breakdown)
+    struct Ev { int kind; cudaEvent_t a, b; };
+    std::vector<Ev> events;
+    // multi-GPU (vpt_comm.cpp): NCCL communicator + gather targets; null for a single rank
+    void*  nccl_comm = nullptr;
+    void*  d_gathered = nullptr; size_t cap_gathered = 0;      // [rank][local pixel] staging of the all-gather
+    void*  d_full_accum = nullptr;                              // caller-owned full frame float3 [H][W] (gather target), may be null
+    void*  d_full_display = nullptr;                            // caller-owned full frame u32 [H][W], may be null
+    void*  d_gathered_disp = nullptr; size_t cap_gathered_disp = 0;
+    cudaStream_t comm_stream = nullptr; cudaEvent_t ev_render_done = nullptr, ev_gather_done = nullptr;
+    int    gather_async = 0;                                    // option "gather_async": gather on the side stream (see vpt_comm_wait)
+    bool   gather_pending = false;
+    size_t max_scratch_bytes = (size_t)12 << 30;                // cap of the per-chunk ray queue + sample planes
+    int    chunk_auto = 1;                                      // passes_per_chunk not set by the caller: pick by local frame size
+};
+
+
 namespace vpt {
 
 // ---- device-side builders (vpt_octree.cu) ---------------------------------------------------------------
@@ -37,5 +91,10 @@ struct SceneEntry {
 bool scene_registry_find(vpt_devptr_t d_root, SceneEntry* out);
 
 int  fail_global(int code, const std::string& msg);     // records the text for vpt_last_error(NULL)
+int  fail_ctx(vpt_context* ctx, int code, const std::string& msg);
+FrameGeom make_frame_geom(const vpt_context* c, unsigned w, unsigned h);
+// after the last resolve of a vpt_render_passes call: all-gather + un-permute into the caller's full-frame buffers (vpt_comm.cpp)
+int  comm_gather_frame(vpt_context* c, const FrameGeom& g, const void* d_local_accum, const void* d_local_display, cudaStream_t stream);
+int  comm_before_accum_write(vpt_context* c, cudaStream_t stream);   // async mode: the previous gather must have read accum
 
 } // namespace vpt

@@ -130,28 +130,47 @@ class Renderer:
 
 
 class DistributedRenderer:
-    """Frame sharded over torch.distributed ranks (one process per GPU); scene replicated on each.
+    """Frame sharded over the ranks of a torch.distributed job (one process per GPU); scene replicated on each.
 
-    Pixels are independent and every Philox stream is keyed by the GLOBAL pixel index, so the gathered
-    frame is bit-identical to a single-GPU render whatever the partition."""
+    torch.distributed is only the BOOTSTRAP here (it carries the 128-byte NCCL id from rank 0 to the others); the exchange
+    itself -- one ncclAllGather of the rank-local accumulators per render call + the stripe un-permutation -- is issued by the
+    C++ library behind the last kernel of the call (vpt_comm_*).  Pixels are independent and every Philox stream is keyed by
+    the GLOBAL pixel index, so the gathered frame is bit-identical to a single-GPU render whatever the partition."""
 
-    def __init__(self, scene: Scene, width, height, cam=None, kp=None, stripe_rows=16, options=None):
+    def __init__(self, scene: Scene, width, height, cam=None, kp=None, stripe_rows=16, options=None, gather_display=False):
         import torch.distributed as dist
         self.dist = dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.r = Renderer(scene, width, height, cam=cam, kp=kp, rank=self.rank, n_ranks=self.world,
                           stripe_rows=stripe_rows, options=options)
-        self.gathered = torch.empty(self.world * self.r.n_local, 3, dtype=torch.float32, device=scene.device)
-
-    def render(self, n_passes):
-        self.r.render(n_passes)
+        self.full = torch.zeros(self.r.height * self.r.width, 3, dtype=torch.float32, device=scene.device)
+        self.full_display = torch.zeros(self.r.height * self.r.width, dtype=torch.int32, device=scene.device) if gather_display else None
+        self.collective_note = "none (1 rank)"
         if self.world > 1:
-            self.dist.all_gather_into_tensor(self.gathered, self.r.buffers.accum)     # the one collective of the path
-        else:
-            self.gathered.copy_(self.r.buffers.accum)
+            idb = torch.zeros(128, dtype=torch.uint8)
+            if self.rank == 0:
+                raw = (C.c_ubyte * 128)()
+                check(lib.vpt_comm_get_unique_id(raw), None, "vpt_comm_get_unique_id")
+                idb = torch.tensor(list(raw), dtype=torch.uint8)
+            idb = idb.to(scene.device); dist.broadcast(idb, src=0)          # bootstrap only
+            raw = (C.c_ubyte * 128)(*idb.cpu().tolist())
+            check(lib.vpt_comm_init(self.r.ctx, raw, self.rank, self.world, stripe_rows), self.r.ctx, "vpt_comm_init")
+            check(lib.vpt_comm_set_gather(self.r.ctx, C.c_void_p(self.full.data_ptr()),
+                                          C.c_void_p(self.full_display.data_ptr()) if gather_display else None), self.r.ctx, "vpt_comm_set_gather")
+            v = C.c_int(0); lib.vpt_comm_info(self.r.ctx, C.byref(v), None, None)
+            self.collective_note = (f"1 ncclAllGather (NCCL {v.value}) of the float3 accumulators per step, issued by libvpt_b200.so behind the last "
+                                    "resolve kernel, + stripe un-permutation kernel")
+
+    def render(self, n_passes, stream=None):
+        self.r.render(n_passes, stream=stream)                               # the gather is part of the call
+        if self.world == 1:
+            self.full.copy_(self.r.buffers.accum)
 
     def full_accum(self):
-        return self.r.unpermute(self.gathered, 3).view(self.r.height, self.r.width, 3)
+        return self.full.view(self.r.height, self.r.width, 3)
+
+    def close(self):
+        self.r.close()
 
 
 def stripe_rows_of_rank(height, rank, n_ranks, stripe_rows):
