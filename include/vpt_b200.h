@@ -103,7 +103,7 @@ int  vpt_get_stats(vpt_context* ctx, unsigned long long* kernel_launches_total, 
 
 /* Instrumentation.  Option "count_stats" = 1 makes the trace kernel accumulate out[0] volume lookups,
  * out[1] lane-steps, out[2] warp step-loop iterations, out[3] rays serviced, out[4] warp service rounds, out[5] rays
- * fetched from the queue (SIMT efficiency of the step loop = out[1] / (32 * out[2])).  Option "profile" = 1 brackets every kernel with
+ * fetched from the queue, out[6] bricks staged by TMA (fast mode) (SIMT efficiency of the step loop = out[1] / (32 * out[2])).  Option "profile" = 1 brackets every kernel with
  * CUDA events: ms/n[0..3] = generate, trace, resolve, blue-noise advance.  Both calls synchronise the device. */
 int  vpt_get_counters(vpt_context* ctx, unsigned long long out[8], int reset);
 int  vpt_get_kernel_times(vpt_context* ctx, float ms[4], int n[4]);
@@ -115,6 +115,30 @@ int  vpt_get_kernel_times(vpt_context* ctx, float ms[4], int n[4]);
  * an opaque array handle for vpt_texture_destroy. */
 int  vpt_texture_create_3d(const float* host_data, int channels, int dim_x, int dim_y, int dim_z,
                            vpt_tex_t* tex_out, void** array_out);
+/* Same texture from a dense grid that already lives in device memory (x fastest), e.g. a procedural grid of several GiB. */
+int  vpt_texture_create_3d_from_device(const float* d_data, int channels, int dim_x, int dim_y, int dim_z,
+                                       vpt_tex_t* tex_out, void** array_out);
+/* Procedural density grid: the reference's fill_volume_buffer (texture_kernels.cu:76-128) for noise_type 0 =
+ * cudaNoise::perlinNoise(pos, scale, seed) at voxel (x, y, z), x fastest -- with ZERO sub-voxel jitter (the reference draws
+ * its jitter from an uninitialised generator state, quirk Q14).  d_buffer: dx*dy*dz floats in device memory.  The matching
+ * VDB_INFO is what GPU_PROC_VOL::create_volume fills (gpu_vdb.cpp:529-541): bmin = box min, bmax = bmin + dim, voxelsize = res,
+ * max_density 1, min_density 0, xform = scale(res). */
+int  vpt_procedural_fill(float* d_buffer, int dim_x, int dim_y, int dim_z, int noise_type, float scale, int seed, void* stream);
+
+/* ---- fast mode for volumes that fit no cache: brick pool + TMA-staged software sampler --------------------------------
+ * vpt_bricks_create re-lays a dense device grid as 4x4x4-cell bricks stored with their +1 apron (5x5x5 texels + brick max /
+ * min: 512 contiguous bytes each, edge texels clamped like the reference's clamp-addressed texture).  vpt_set_brick_volume
+ * makes the context trace volume 0 from that pool: k_trace_brick stages the brick under each ray into shared memory with
+ * one cp.async.bulk (TMA) and filters it in software with the texture unit's weight rule (8-bit fractions).  This is NOT
+ * bit-identical to the tex3D path -- look-ups may differ in the last bits, so a few samples per million take another branch
+ * of the delta tracker -- and is validated statistically (tests/test_bricks_gpu.py).  Supported: a vpt_octree_build scene
+ * of one volume without colour grid, direct integrator, no emission, no point lights; anything else is refused with
+ * VPT_ERR_UNSUPPORTED.  d_pool = 0 returns the context to parity mode (tex3D). */
+int  vpt_bricks_create(const float* d_dense, int dim_x, int dim_y, int dim_z, vpt_devptr_t* d_pool_out, unsigned long long* bytes_out);
+int  vpt_bricks_read(vpt_devptr_t d_pool, unsigned long long first_brick, unsigned long long n_bricks, float* h_out);   /* 128 floats per brick */
+int  vpt_bricks_destroy(vpt_devptr_t d_pool);
+int  vpt_set_brick_volume(vpt_context* ctx, vpt_devptr_t d_pool, int dim_x, int dim_y, int dim_z);
+
 /* Equirectangular environment map float4 (main.cpp:945-978: wrap / clamp, linear, normalised). */
 int  vpt_texture_create_env(const float* host_rgba, unsigned width, unsigned height, vpt_tex_t* tex_out, void** array_out);
 /* The four sky-sampling tables the volumetric path integrator reads when environment_type == 0 (reference create_cdf,

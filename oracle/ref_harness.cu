@@ -9,6 +9,8 @@
  *     the reference `build_octree` (source/bvh/bvh_kernels.cu:582-604, device-heap recursion).
  *   - vptref_build_bvh    : the reference LBVH (`BuildBVH`, bvh_kernels.cu:460-580), N >= 2 only
  *     (for N == 1 the reference dereferences an unwritten parent pointer).
+ *   - vptref_fill_volume  : the reference's fill_volume_buffer (texture_kernels.cu, compiled unmodified into
+ *     texture_kernels_ref.cubin) with the launch shape of gpu_vdb.cpp:547-552.
  *   - vptref_bn_advance   : launches `bn_advance_ref`, a kernel generated at build time from the
  *     reference's own blue-noise update statements (render_kernel.cu:2321-2324), used together
  *     with the "nobn" oracle build that has that block compiled out (race-free protocol, Q6).
@@ -77,6 +79,20 @@ int vptref_load_bn_kernel(const char* cubin_path) {
     CKR(cudaFree(0));
     CK(cuModuleLoad(&g_bn_mod, cubin_path));
     CK(cuModuleGetFunction(&g_bn_fn, g_bn_mod, "bn_advance_ref"));
+    return 0;
+}
+
+// The reference's procedural density fill (source/texture_kernels.cu:76-128) launched as GPU_PROC_VOL::create_volume does
+// (gpu_vdb.cpp:547-552: block 8x8x8, grid dim/8 + 1).  Its sub-voxel jitter comes from an UNINITIALISED curand state (quirk Q14).
+static CUmodule g_tex_mod = nullptr;
+static CUfunction g_fill_fn = nullptr;
+int vptref_fill_volume(const char* cubin_path, void* d_buffer, int dx, int dy, int dz, float scale, int noise_type) {
+    CKR(cudaFree(0));
+    if (!g_fill_fn) { CK(cuModuleLoad(&g_tex_mod, cubin_path)); CK(cuModuleGetFunction(&g_fill_fn, g_tex_mod, "fill_volume_buffer")); }
+    int3 dims = make_int3(dx, dy, dz);
+    void* params[] = { &d_buffer, &dims, &scale, &noise_type };
+    CK(cuLaunchKernel(g_fill_fn, dx / 8 + 1, dy / 8 + 1, dz / 8 + 1, 8, 8, 8, 0, NULL, params, NULL));
+    CKR(cudaDeviceSynchronize());
     return 0;
 }
 

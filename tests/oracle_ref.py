@@ -37,6 +37,7 @@ class RefOracle:
         L.vptref_build_octree.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]; L.vptref_build_octree.restype = C.c_int
         L.vptref_build_bvh.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_float)]
         L.vptref_build_bvh.restype = C.c_int
+        L.vptref_fill_volume.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]; L.vptref_fill_volume.restype = C.c_int
         L.vptref_sizes.argtypes = [C.POINTER(C.c_size_t), C.c_int]; L.vptref_sizes.restype = C.c_int
         L.vptref_update_camera.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float]
         L.vptref_bounds.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -59,6 +60,12 @@ class RefOracle:
             if rc: raise RuntimeError(f"vptref_atmosphere_init -> {rc}")
             _ATMO_CACHE[key] = bytes(buf)
         C.memmove(C.byref(atmos), _ATMO_CACHE[key], 464)
+
+    def fill_volume(self, d_buffer_ptr, dims, scale=0.1, noise_type=0):
+        """The reference's fill_volume_buffer into a device buffer of dims[0]*dims[1]*dims[2] floats."""
+        p = os.path.join(REF_DIR, "texture_kernels_ref.cubin")
+        rc = self.lib.vptref_fill_volume(p.encode(), C.c_void_p(d_buffer_ptr), int(dims[0]), int(dims[1]), int(dims[2]), float(scale), int(noise_type))
+        if rc: raise RuntimeError(f"vptref_fill_volume -> {rc}")
 
     def load_kernels(self):
         if self._loaded:

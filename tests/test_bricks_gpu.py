@@ -1,0 +1,156 @@
+"""BASELINE configs[3] (procedural Perlin grid) -- the volume ingest (row N3) and the brick / TMA "fast mode" of the trace stage.
+
+  * vpt_procedural_fill against the reference's own fill_volume_buffer (texture_kernels.cu compiled into oracle/_ref).  The
+    reference jitters each voxel by an UNDEFINED sub-voxel offset (uninitialised curand state, quirk Q14) of at most 1/dim of
+    a voxel; ours uses zero jitter, so the two grids agree to ~|grad| * scale / dim, not bit for bit: tolerance 2e-3.
+  * parity mode (tex3D) on the procedural volume against the reference kernel: the usual per-seed tolerance.
+  * the brick pool layout, texel for texel.
+  * fast mode (bricks staged by cp.async.bulk, software filter with the texture unit's 8-bit weight rule): STATISTICAL parity,
+    as SURVEY 8(c) prescribes -- the fraction of decision-flipped pixels per pass is bounded and reported, and the converged
+    image is as close to the reference as the reference is to itself under another random stream (RMSE <= 1.1 x noise floor).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import vpt_b200 as V
+from vpt_b200.scene import synthetic_env
+import oracle_ref
+from test_parity_gpu import flipped_fraction, make_kp, MAX_FLIPPED, needs_ref
+
+pytestmark = pytest.mark.gpu
+has_fill = os.path.exists(os.path.join(oracle_ref.REF_DIR, "texture_kernels_ref.cubin"))
+
+
+@pytest.fixture(scope="module")
+def perlin():
+    vol = V.Volume.procedural((96, 80, 72), scale=0.1, seed=123)
+    vol.build_bricks()
+    return vol
+
+
+def scene_of(vol):
+    return V.Scene([vol.instance()], env=synthetic_env(512, 256), keep=[vol])
+
+
+@needs_ref
+@pytest.mark.skipif(not has_fill, reason="oracle/_ref/texture_kernels_ref.cubin not built")
+def test_procedural_fill_against_reference_fill_kernel():
+    dims = (70, 52, 44)                                       # ragged: not multiples of the reference's 8x8x8 blocks
+    vol = V.Volume.procedural(dims, scale=0.1, seed=123)
+    ref = torch.full((dims[0] * dims[1] * dims[2],), -7.0, dtype=torch.float32, device="cuda")
+    oracle_ref.RefOracle().fill_volume(ref.data_ptr(), dims, scale=0.1, noise_type=0)
+    a = vol.dense.cpu().numpy(); b = ref.cpu().numpy()
+    assert np.isfinite(a).all() and a.min() < -0.3 and a.max() > 0.3, "Perlin noise spans negative and positive densities (quirk Q10)"
+    print(f"fill: max |ours - reference| = {np.abs(a - b).max():.3g} (jitter bound ~ {0.1 / min(dims) * 2:.3g}), corr {np.corrcoef(a, b)[0, 1]:.6f}")
+    assert np.abs(a - b).max() < 2e-3
+    info = vol.rec.vdb_info
+    assert (info.max_density, info.min_density, info.voxelsize) == (1.0, 0.0, 1.0) and (info.dim.x, info.dim.y, info.dim.z) == dims
+    assert info.bmax.x - info.bmin.x == dims[0]
+
+
+def test_brick_pool_layout(perlin):
+    dx, dy, dz = perlin.dims
+    dense = perlin.dense.cpu().numpy().reshape(dz, dy, dx)
+    nbx, nby, nbz = (dx + 3) // 4, (dy + 3) // 4, (dz + 3) // 4
+    assert perlin.brick_bytes == nbx * nby * nbz * 512
+    pool = np.empty(perlin.brick_bytes // 4, dtype=np.float32)
+    V._native.check(V.lib.vpt_bricks_read(perlin.brick_pool, 0, nbx * nby * nbz, pool.ctypes.data_as(C.POINTER(C.c_float))), None, "vpt_bricks_read")
+    pool = pool.reshape(nbz, nby, nbx, 128)
+    rng = np.random.RandomState(0)
+    for _ in range(200):
+        bx, by, bz = rng.randint(nbx), rng.randint(nby), rng.randint(nbz)
+        zz = np.minimum(bz * 4 + np.arange(5), dz - 1); yy = np.minimum(by * 4 + np.arange(5), dy - 1); xx = np.minimum(bx * 4 + np.arange(5), dx - 1)
+        want = dense[np.ix_(zz, yy, xx)].reshape(-1)           # [lz][ly][lx], apron clamped at the grid edge
+        got = pool[bz, by, bx]
+        assert np.array_equal(got[:125], want)
+        assert got[125] == want.max() and got[126] == want.min() and got[127] == 0.0
+
+
+@needs_ref
+def test_parity_mode_on_the_procedural_volume_against_reference(perlin):
+    """tex3D path, negative densities included: per-seed parity with the reference kernel."""
+    scene = scene_of(perlin)
+    kw = dict(ray_depth=3, volume_depth=2)
+    mine = V.Renderer(scene, 320, 200, kp=make_kp(**kw)); ref = V.Renderer(scene, 320, 200, kp=make_kp(**kw), cam=mine.cam)
+    orc = oracle_ref.RefOracle()
+    ref.params.p_oct.value = orc.build_octree(scene.h_volumes, 1)
+    scene.reset_blue_noise(); orc.render(ref, 3)
+    scene.reset_blue_noise(); mine.render(3); torch.cuda.synchronize()
+    want = ref.buffers.accum.cpu().numpy()
+    assert float(want.mean()) > 1e-3
+    assert flipped_fraction(mine.buffers.accum.cpu().numpy(), want) <= MAX_FLIPPED
+
+
+def test_fast_mode_statistics_against_parity_mode(perlin):
+    """Same seeds, same control flow: a pixel differs only where a software-filtered density landed on the other side of an
+    accept / reject comparison.  Report the flipped fraction of ONE pass and bound it."""
+    scene = scene_of(perlin)
+    kw = dict(ray_depth=2)
+    par = V.Renderer(scene, 640, 400, kp=make_kp(**kw)); fast = V.Renderer(scene, 640, 400, kp=make_kp(**kw), cam=par.cam, options={"count_stats": 1})
+    fast.set_brick_volume(perlin)
+    scene.reset_blue_noise(); par.render(1)
+    scene.reset_blue_noise(); fast.render(1); torch.cuda.synchronize()
+    a = par.buffers.accum.cpu().numpy(); b = fast.buffers.accum.cpu().numpy()
+    frac = flipped_fraction(b, a)
+    cnt = fast.counters()
+    print(f"fast vs parity, 1 pass: flipped {frac:.4g}; {cnt['lookups']} look-ups, {cnt['brick_fetches']} bricks staged by TMA "
+          f"({cnt['lookups'] / max(1, cnt['brick_fetches']):.2f} look-ups per staged brick), {cnt['rays']} rays")
+    assert cnt["brick_fetches"] > 0 and cnt["lookups"] >= cnt["brick_fetches"]
+    assert np.isfinite(b).all() and frac <= 0.02
+    assert abs(float(b.mean()) - float(a.mean())) <= 0.01 * float(a.mean())
+    # depth buffer: first-hit distance only moves where the first walk's decisions moved
+    assert flipped_fraction(fast.buffers.depth.cpu().numpy()[:, None], par.buffers.depth.cpu().numpy()[:, None]) <= 0.02
+
+
+@needs_ref
+def test_fast_mode_converged_error_within_reference_noise_floor(perlin):
+    """converged (64 spp) RMSE of fast mode against the reference <= 1.1 x the reference-vs-reference RMSE obtained
+    with a different `iteration` base (another set of Philox streams)."""
+    scene = scene_of(perlin)
+    W, H, P = 200, 120, 64
+    kw = dict(ray_depth=2)
+    fast = V.Renderer(scene, W, H, kp=make_kp(**kw)); fast.set_brick_volume(perlin)
+    ra = V.Renderer(scene, W, H, kp=make_kp(**kw), cam=fast.cam); rb = V.Renderer(scene, W, H, kp=make_kp(**kw), cam=fast.cam)
+    orc = oracle_ref.RefOracle()
+    root = orc.build_octree(scene.h_volumes, 1)
+    ra.params.p_oct.value = root; rb.params.p_oct.value = root
+    scene.reset_blue_noise(); fast.render(P)
+    scene.reset_blue_noise(); orc.render(ra, P)
+    # second reference run on other random streams: passes 1000 .. 1000+P-1 (accumulated by hand: the running mean needs iteration 0..)
+    acc = torch.zeros_like(rb.buffers.accum)
+    scene.reset_blue_noise()
+    for p in range(P):
+        rb.kp.iteration = 0; rb.buffers.accum.zero_()
+        # one pass with the stream of pass 1000 + p: curand offset = iteration * 4096, so render it as "iteration 1000 + p" into a
+        # zeroed accumulator would average with 1/(it+1); use max_interactions to keep iteration small instead: shift the seed via
+        # the resolution-independent trick of running P extra warm-up passes is too slow, so take the single-pass value directly
+        rb.kp.iteration = 1000 + p
+        orc.launch(rb.params.array, W, H, orc.NOBN); orc.bn_advance(rb.kp)
+        torch.cuda.synchronize()
+        # accum = 0 + (value - 0) / (it + 1)  ->  value = accum * (it + 1)
+        acc += rb.buffers.accum * float(1000 + p + 1)
+    acc /= P
+    torch.cuda.synchronize()
+    a = ra.buffers.accum.cpu().numpy(); f = fast.buffers.accum.cpu().numpy(); b = acc.cpu().numpy()
+    rmse = lambda x, y: float(np.sqrt(np.mean((x - y) ** 2)))
+    floor, err = rmse(b, a), rmse(f, a)
+    print(f"converged {P} spp: RMSE fast-vs-reference {err:.4g}, reference-vs-reference (other streams) {floor:.4g}")
+    assert floor > 0 and err <= 1.1 * floor
+    assert abs(float(f.mean()) - float(a.mean())) <= 0.01 * float(a.mean())
+
+
+def test_fast_mode_refuses_what_it_does_not_implement(perlin):
+    scene = scene_of(perlin)
+    r = V.Renderer(scene, 64, 64, kp=make_kp(ray_depth=1, integrator=1))
+    r.set_brick_volume(perlin)
+    with pytest.raises(V.VptError, match="fast"):
+        r.render_pass()
+    two = V.Scene([perlin.instance(), perlin.instance(pos=(200, 0, 0))], env=synthetic_env(512, 256), keep=[perlin])
+    r2 = V.Renderer(two, 64, 64, kp=make_kp(ray_depth=1)); r2.set_brick_volume(perlin)
+    with pytest.raises(V.VptError, match="fast"):
+        r2.render_pass()
+    r2.set_brick_volume(None); r2.render_pass(); torch.cuda.synchronize()       # parity mode still works on that scene

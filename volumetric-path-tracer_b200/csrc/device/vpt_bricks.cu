@@ -1,0 +1,112 @@
+// vpt_bricks.cu -- volume ingest for the HBM-bound configuration (BASELINE configs[3]):
+//   k_fill_perlin   procedural density grid, restating the reference's fill_volume_buffer (source/texture_kernels.cu:76-128,
+//                   noise type 0 = cudaNoise::perlinNoise, thirdparty/cuda-noise/include/cuda_noise.cuh:574-619) with ZERO
+//                   jitter (the reference draws its sub-voxel jitter from an uninitialised curand state: quirk Q14, undefined)
+//   k_build_bricks  dense x-fastest grid -> pool of 4x4x4-cell bricks, each stored with its +1 apron as 5x5x5 texels
+//                   (125 floats) + [125] brick max, [126] brick min, [127] 0  = 128 floats = 512 bytes, 512-byte aligned:
+//                   one contiguous cp.async.bulk (TMA, SASS UBLKCP) brings everything a trilinear look-up inside the brick
+//                   needs into shared memory.  Texel indices past the grid edge are clamped when the brick is built, which
+//                   is exactly the clamp addressing of the reference's texture (gpu_vdb.cpp:586-588).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+namespace vpt {
+
+// ---- cuda-noise restatement (hash, gradient, fade; cuda_noise.cuh:37-48, 119-122, 178-206) ------------------------
+__device__ inline unsigned int noise_hash(unsigned int seed)
+{
+    seed = (seed + 0x7ed55d16) + (seed << 12);
+    seed = (seed ^ 0xc761c23c) ^ (seed >> 19);
+    seed = (seed + 0x165667b1) + (seed << 5);
+    seed = (seed + 0xd3a2646c) ^ (seed << 9);
+    seed = (seed + 0xfd7046c5) + (seed << 3);
+    seed = (seed ^ 0xb55a4f09) ^ (seed >> 16);
+    return seed;
+}
+
+__device__ inline unsigned int noise_grid(float x, float y, float z, float seed)
+{
+    return noise_hash((unsigned int)(x * 1723.0f + y * 93241.0f + z * 149812.0f + 3824 + seed));
+}
+
+__device__ inline float noise_grad(int hash, float x, float y, float z)
+{
+    switch (hash & 0xF) {
+    case 0x0: return x + y;   case 0x1: return -x + y;  case 0x2: return x - y;   case 0x3: return -x - y;
+    case 0x4: return x + z;   case 0x5: return -x + z;  case 0x6: return x - z;   case 0x7: return -x - z;
+    case 0x8: return y + z;   case 0x9: return -y + z;  case 0xA: return y - z;   case 0xB: return -y - z;
+    case 0xC: return y + x;   case 0xD: return -y + z;  case 0xE: return y - x;   default:  return -y - z;
+    }
+}
+
+__device__ inline float noise_fade(float t) { return t * t * t * (t * (t * 6.0f - 15.0f) + 10.0f); }
+__device__ inline float noise_lerp(float a, float b, float r) { return a * (1.0f - r) + b * r; }
+
+__device__ float perlin_noise(float px, float py, float pz, float scale, int seed)
+{
+    const float fseed = (float)seed;
+    px *= scale; py *= scale; pz *= scale;
+    const float ix = floorf(px), iy = floorf(py), iz = floorf(pz);
+    px -= ix; py -= iy; pz -= iz;
+    const float u = noise_fade(px), v = noise_fade(py), w = noise_fade(pz);
+    const float i000 = noise_grad(noise_grid(ix, iy, iz, fseed), px, py, pz);
+    const float i100 = noise_grad(noise_grid(ix + 1.0f, iy, iz, fseed), px - 1.0f, py, pz);
+    const float i010 = noise_grad(noise_grid(ix, iy + 1.0f, iz, fseed), px, py - 1.0f, pz);
+    const float i110 = noise_grad(noise_grid(ix + 1.0f, iy + 1.0f, iz, fseed), px - 1.0f, py - 1.0f, pz);
+    const float i001 = noise_grad(noise_grid(ix, iy, iz + 1.0f, fseed), px, py, pz - 1.0f);
+    const float i101 = noise_grad(noise_grid(ix + 1.0f, iy, iz + 1.0f, fseed), px - 1.0f, py, pz - 1.0f);
+    const float i011 = noise_grad(noise_grid(ix, iy + 1.0f, iz + 1.0f, fseed), px, py - 1.0f, pz - 1.0f);
+    const float i111 = noise_grad(noise_grid(ix + 1.0f, iy + 1.0f, iz + 1.0f, fseed), px - 1.0f, py - 1.0f, pz - 1.0f);
+    const float x00 = noise_lerp(i000, i100, u), x10 = noise_lerp(i010, i110, u);
+    const float x01 = noise_lerp(i001, i101, u), x11 = noise_lerp(i011, i111, u);
+    return noise_lerp(noise_lerp(x00, x10, v), noise_lerp(x01, x11, v), w);
+}
+
+// one thread per voxel, x fastest (idx = x + dims.x * (y + dims.y * z), texture_kernels.cu:84); a warp writes 32 consecutive floats
+__global__ void k_fill_perlin(float* __restrict__ buffer, int3 dims, float scale, int seed)
+{
+    const size_t total = (size_t)dims.x * dims.y * dims.z;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % dims.x), y = (int)((i / dims.x) % dims.y), z = (int)(i / ((size_t)dims.x * dims.y));
+        buffer[i] = perlin_noise((float)x, (float)y, (float)z, scale, seed);
+    }
+}
+
+// one warp per brick: lanes cover the 125 texels in four rounds, min / max by shuffle
+__global__ void k_build_bricks(const float* __restrict__ dense, int3 dims, int3 nb, float* __restrict__ bricks)
+{
+    const size_t brick = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const size_t n_bricks = (size_t)nb.x * nb.y * nb.z;
+    if (brick >= n_bricks) return;
+    const int bx = (int)(brick % nb.x), by = (int)((brick / nb.x) % nb.y), bz = (int)(brick / ((size_t)nb.x * nb.y));
+    float* out = bricks + brick * 128;
+    float mx = -FLT_MAX, mn = FLT_MAX;
+    for (int t = lane; t < 125; t += 32) {
+        const int lx = t % 5, ly = (t / 5) % 5, lz = t / 25;
+        const int x = min(bx * 4 + lx, dims.x - 1), y = min(by * 4 + ly, dims.y - 1), z = min(bz * 4 + lz, dims.z - 1);
+        const float v = dense[((size_t)z * dims.y + y) * dims.x + x];
+        out[t] = v;
+        mx = fmaxf(mx, v); mn = fminf(mn, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
+    if (lane == 0) { out[125] = mx; out[126] = mn; out[127] = 0.0f; }
+}
+
+cudaError_t launch_fill_perlin(float* d_buffer, int dx, int dy, int dz, float scale, int seed, cudaStream_t s)
+{
+    k_fill_perlin<<<148 * 16, 256, 0, s>>>(d_buffer, make_int3(dx, dy, dz), scale, seed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_bricks(const float* d_dense, int dx, int dy, int dz, float* d_bricks, cudaStream_t s)
+{
+    const int3 nb = make_int3((dx + 3) / 4, (dy + 3) / 4, (dz + 3) / 4);
+    const size_t n = (size_t)nb.x * nb.y * nb.z;
+    const size_t blocks = (n * 32 + 255) / 256;
+    k_build_bricks<<<(unsigned)blocks, 256, 0, s>>>(d_dense, make_int3(dx, dy, dz), nb, d_bricks);
+    return cudaGetLastError();
+}
+
+} // namespace vpt

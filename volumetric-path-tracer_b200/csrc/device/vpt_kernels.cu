@@ -329,6 +329,7 @@ k_generate(const FrameArgs fa)
 }
 
 #include "vpt_trace.cuh"
+#include "vpt_trace_brick.cuh"
 
 // =====================================================================================================
 // k_resolve
@@ -539,12 +540,25 @@ static cudaError_t trace_init_t(int* max_ctas)
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_ctas, k_trace<kInteg, kLean>, kTraceThreads, trace_smem_bytes());
 }
 
-cudaError_t trace_kernels_init(int max_ctas[3])
+static size_t brick_smem_bytes() { return (size_t)kBrickThreads * kBrickBytes; }
+
+cudaError_t trace_kernels_init(int max_ctas[4])
 {
     cudaError_t e = trace_init_t<0, false>(&max_ctas[0]);
     if (e == cudaSuccess) e = trace_init_t<0, true>(&max_ctas[1]);
     if (e == cudaSuccess) e = trace_init_t<1, false>(&max_ctas[2]);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brick_smem_bytes());
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas[3], k_trace_brick, kBrickThreads, brick_smem_bytes());
     return e;
+}
+
+cudaError_t launch_trace_brick(const FrameArgs& fa, const float* pool, const int dims[3], int n_ctas, cudaStream_t s)
+{
+    BrickArgs ba;
+    ba.pool = pool; ba.dimx = dims[0]; ba.dimy = dims[1]; ba.dimz = dims[2];
+    ba.nbx = (dims[0] + 3) / 4; ba.nby = (dims[1] + 3) / 4; ba.nbz = (dims[2] + 3) / 4;
+    k_trace_brick<<<n_ctas, kBrickThreads, brick_smem_bytes(), s>>>(fa, ba);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_resolve(const FrameArgs& fa, const vpt_atmosphere* sky, int n_passes, int sampled, int write_display, cudaStream_t s)

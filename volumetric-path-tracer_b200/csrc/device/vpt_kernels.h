@@ -53,8 +53,12 @@ cudaError_t launch_prepare_volumes(const vpt_gpu_vdb* vols, const SceneTables& h
 cudaError_t launch_generate(const FrameArgs& fa, int n_passes, cudaStream_t s);
 // atm != null selects the volumetric path integrator variant of the trace kernel
 cudaError_t launch_trace(const FrameArgs& fa, const vpt_atmosphere* atm, bool lean, int n_ctas, cudaStream_t s);
-// per device: dynamic shared memory opt-in of the three k_trace instantiations + CTAs per SM of [generic, lean, volumetric path]
-cudaError_t trace_kernels_init(int max_ctas[3]);
+// per device: dynamic shared memory opt-in of the trace kernels + CTAs per SM of [generic, lean, volumetric path, brick]
+cudaError_t trace_kernels_init(int max_ctas[4]);      // [3]: k_trace_brick
+// fast mode: lean direct integrator reading the density from a brick pool (vpt_trace_brick.cuh); dims = voxels per axis
+cudaError_t launch_trace_brick(const FrameArgs& fa, const float* pool, const int dims[3], int n_ctas, cudaStream_t s);
+cudaError_t launch_fill_perlin(float* d_buffer, int dx, int dy, int dz, float scale, int seed, cudaStream_t s);
+cudaError_t launch_build_bricks(const float* d_dense, int dx, int dy, int dz, float* d_bricks, cudaStream_t s);
 // sky != null selects the environment_type == 0 variant (host copy of the caller's AtmosphereParameters)
 cudaError_t launch_resolve(const FrameArgs& fa, const vpt_atmosphere* sky, int n_passes, int sampled, int write_display, cudaStream_t s);
 cudaError_t launch_bn_prepare(void* bn, float2* table, int np, cudaStream_t s);

@@ -262,6 +262,13 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
             c->cached_volumes = d_volumes; c->cached_root = d_root; c->cached_generation = registered ? ent.generation : 0ull;
         }
     }
+    if (c->brick_pool) {
+        // fast mode reads volume 0 from the brick pool: only the lean case of the direct integrator is built for it
+        vpt::SceneEntry ent;
+        const bool ok = vpt::scene_registry_find(d_root, &ent) && ent.n == 1 && !(ent.any_flags & 1u) && !(kp.emission_scale > 0.0f) &&
+                        fa.lights.num_lights == 0 && kp.integrator == 0;
+        if (!ok) return fail(c, VPT_ERR_UNSUPPORTED, "brick (fast) mode needs a vpt_octree_build scene of ONE volume without colour grid, the direct integrator, no emission and no point lights");
+    }
     // "lean" = nothing but one volume, sun and environment in play (the headline configuration)
     const bool lean = c->scene_single_volume && !(kp.emission_scale > 0.0f) && fa.lights.num_lights == 0 && kp.integrator == 0 && !c->force_generic;
 
@@ -302,7 +309,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
     fa.queue_count = c->d_counters; fa.queue_head = c->d_counters + 1;
     fa.planeA = c->d_planeA; fa.planeB = c->d_planeB; fa.planeC = c->d_planeC; fa.planeD = planeD ? c->d_planeD : nullptr;
 
-    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : c->max_ctas[vol_integ ? 2 : (lean ? 1 : 0)];
+    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : c->max_ctas[c->brick_pool ? 3 : vol_integ ? 2 : (lean ? 1 : 0)];
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int trace_ctas = c->num_sms * ctas_per_sm;
 
@@ -325,7 +332,8 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         VPT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned) * 2, stream));
         VPT_CUDA(c, timed(3, [&] { return vpt::launch_bn_prepare((void*)kp.blue_noise_buffer, c->d_bn_table, (int)np, stream); }));   // jitter table + advance
         VPT_CUDA(c, timed(0, [&] { return vpt::launch_generate(fa, (int)np, stream); }));
-        VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, vol_integ ? &atmo : nullptr, lean, trace_ctas, stream); }));
+        if (c->brick_pool) VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace_brick(fa, c->brick_pool, c->brick_dims, trace_ctas, stream); }));
+        else VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, vol_integ ? &atmo : nullptr, lean, trace_ctas, stream); }));
         const bool last = (done + np == n_passes);
         if (c->gather_pending) { int rc = vpt::comm_before_accum_write(c, stream); if (rc != VPT_OK) return rc; }
         VPT_CUDA(c, timed(2, [&] { return vpt::launch_resolve(fa, sky, (int)np, 1, last ? 1 : 0, stream); }));
@@ -401,6 +409,68 @@ int vpt_texture_create_3d(const float* host, int channels, int dx, int dy, int d
     cudaTextureObject_t tex = 0;
     VPT_CUDA(nullptr, cudaCreateTextureObject(&tex, &res, &td, NULL));
     *tex_out = (vpt_tex_t)tex; *array_out = (void*)arr;
+    return VPT_OK;
+}
+
+int vpt_texture_create_3d_from_device(const float* d_data, int channels, int dx, int dy, int dz, vpt_tex_t* tex_out, void** array_out) {
+    if (!d_data || !tex_out || !array_out || (channels != 1 && channels != 4) || dx < 1 || dy < 1 || dz < 1)
+        return fail(nullptr, VPT_ERR_INVALID, "vpt_texture_create_3d_from_device: bad arguments");
+    cudaChannelFormatDesc desc = channels == 1 ? cudaCreateChannelDesc<float>() : cudaCreateChannelDesc<float4>();
+    cudaExtent ext = make_cudaExtent((size_t)dx, (size_t)dy, (size_t)dz);
+    cudaArray_t arr = nullptr;
+    VPT_CUDA(nullptr, cudaMalloc3DArray(&arr, &desc, ext));
+    cudaMemcpy3DParms cp; memset(&cp, 0, sizeof(cp));
+    const size_t esz = sizeof(float) * (size_t)channels;
+    cp.srcPtr = make_cudaPitchedPtr((void*)d_data, (size_t)dx * esz, (size_t)dx, (size_t)dy);
+    cp.dstArray = arr; cp.extent = ext; cp.kind = cudaMemcpyDeviceToDevice;
+    cudaError_t e = cudaMemcpy3D(&cp);
+    cudaResourceDesc res; memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray; res.res.array.array = arr;
+    cudaTextureDesc td; memset(&td, 0, sizeof(td));
+    td.normalizedCoords = 1; td.filterMode = cudaFilterModeLinear;
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t tex = 0;
+    if (e == cudaSuccess) e = cudaCreateTextureObject(&tex, &res, &td, NULL);
+    if (e != cudaSuccess) { cudaFreeArray(arr); return fail(nullptr, VPT_ERR_CUDA, std::string("vpt_texture_create_3d_from_device: ") + cudaGetErrorString(e)); }
+    *tex_out = (vpt_tex_t)tex; *array_out = (void*)arr;
+    return VPT_OK;
+}
+
+int vpt_procedural_fill(float* d_buffer, int dx, int dy, int dz, int noise_type, float scale, int seed, void* stream) {
+    if (!d_buffer || dx < 1 || dy < 1 || dz < 1) return fail(nullptr, VPT_ERR_INVALID, "vpt_procedural_fill: bad arguments");
+    if (noise_type != 0) return fail(nullptr, VPT_ERR_UNSUPPORTED, "vpt_procedural_fill: only noise type 0 (Perlin gradient noise, the reference's default) is built");
+    VPT_CUDA(nullptr, vpt::launch_fill_perlin(d_buffer, dx, dy, dz, scale, seed, (cudaStream_t)stream));
+    return VPT_OK;
+}
+
+int vpt_bricks_create(const float* d_dense, int dx, int dy, int dz, vpt_devptr_t* d_pool_out, unsigned long long* bytes_out) {
+    if (!d_dense || !d_pool_out || dx < 1 || dy < 1 || dz < 1) return fail(nullptr, VPT_ERR_INVALID, "vpt_bricks_create: bad arguments");
+    const size_t nb = (size_t)((dx + 3) / 4) * ((dy + 3) / 4) * ((dz + 3) / 4);
+    if (nb > (size_t)0x7fffffff) return fail(nullptr, VPT_ERR_UNSUPPORTED, "vpt_bricks_create: more than 2^31 bricks");
+    float* pool = nullptr;
+    VPT_CUDA(nullptr, cudaMalloc(&pool, nb * 512));
+    cudaError_t e = vpt::launch_build_bricks(d_dense, dx, dy, dz, pool, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(pool); return fail(nullptr, VPT_ERR_CUDA, std::string("vpt_bricks_create: ") + cudaGetErrorString(e)); }
+    *d_pool_out = (vpt_devptr_t)(uintptr_t)pool;
+    if (bytes_out) *bytes_out = (unsigned long long)nb * 512ull;
+    return VPT_OK;
+}
+
+int vpt_bricks_read(vpt_devptr_t d_pool, unsigned long long first_brick, unsigned long long n_bricks, float* h_out) {
+    if (!d_pool || !h_out) return fail(nullptr, VPT_ERR_INVALID, "vpt_bricks_read: null argument");
+    VPT_CUDA(nullptr, cudaMemcpy(h_out, reinterpret_cast<const char*>((uintptr_t)d_pool) + first_brick * 512ull, n_bricks * 512ull, cudaMemcpyDeviceToHost));
+    return VPT_OK;
+}
+
+int vpt_bricks_destroy(vpt_devptr_t d_pool) { if (d_pool) cudaFree((void*)(uintptr_t)d_pool); return VPT_OK; }
+
+int vpt_set_brick_volume(vpt_context* c, vpt_devptr_t d_pool, int dx, int dy, int dz) {
+    if (!c) return VPT_ERR_INVALID;
+    if (d_pool && (dx < 1 || dy < 1 || dz < 1)) return fail(c, VPT_ERR_INVALID, "vpt_set_brick_volume: bad dimensions");
+    c->brick_pool = reinterpret_cast<const float*>((uintptr_t)d_pool);
+    c->brick_dims[0] = dx; c->brick_dims[1] = dy; c->brick_dims[2] = dz;
     return VPT_OK;
 }
 

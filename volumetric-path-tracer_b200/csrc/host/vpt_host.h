@@ -24,7 +24,8 @@ struct vpt_context {
     bool   scene_single_volume = false;
     size_t cap_vrec = 0;              // VolumeRec capacity (grows with the instance count)
     int*   h_pinned = nullptr;        // one pinned word for the 4-byte read-back a foreign octree needs
-    int    max_ctas[3] = {0, 0, 0};   // k_trace occupancy per instantiation: [0] generic, [1] lean, [2] volumetric path
+    int    max_ctas[4] = {0, 0, 0, 0};   // trace kernel occupancy: [0] generic, [1] lean, [2] volumetric path, [3] brick (fast mode)
+    const float* brick_pool = nullptr; int brick_dims[3] = {0, 0, 0};   // fast mode: density of volume 0 as a brick pool (vpt_set_brick_volume)
     int    force_generic = 0;        // option "generic_kernel": 1 = never use the lean trace instantiation (A/B and tests)
     vpt::SceneTables* d_scene = nullptr;
     vpt::OctInternal* d_internal = nullptr;
@@ -87,6 +88,7 @@ struct SceneEntry {
     int*         d_leaf_indices = nullptr;   // CSR payload (at least 1 element)
     size_t       total_indices = 0;
     int          max_leaf_count = 0;
+    unsigned     any_flags = 0;              // bit0: some instance has a colour grid, bit1: some instance has an emission grid
 };
 bool scene_registry_find(vpt_devptr_t d_root, SceneEntry* out);
 

@@ -66,6 +66,7 @@ int vpt_octree_build(const vpt_gpu_vdb* h_volumes, int n, vpt_devptr_t* d_root_o
     root->bbox.pmax = { -3.402823466e+38F, -3.402823466e+38F, -3.402823466e+38F };
     root->max_extinction = .0f; root->min_extinction = 3.402823466e+38F; root->voxel_size = 3.402823466e+38F;
     root->depth = 4;
+    unsigned any_flags = 0;
     for (int i = 0; i < n; ++i) {
         float b[6]; vpt::instance_bounds_host(h_volumes[i], b);
         root->bbox.pmax.x = fmaxf(root->bbox.pmax.x, b[3]); root->bbox.pmax.y = fmaxf(root->bbox.pmax.y, b[4]); root->bbox.pmax.z = fmaxf(root->bbox.pmax.z, b[5]);
@@ -75,6 +76,7 @@ int vpt_octree_build(const vpt_gpu_vdb* h_volumes, int n, vpt_devptr_t* d_root_o
         root->max_extinction = fmaxf(root->max_extinction, h_volumes[i].vdb_info.max_density);
         root->min_extinction = fminf(root->min_extinction, h_volumes[i].vdb_info.min_density);
         root->has_children = 1;
+        any_flags |= (h_volumes[i].vdb_info.has_color ? 1u : 0u) | (h_volumes[i].vdb_info.has_emission ? 2u : 0u);
     }
     root->bbox.pmax.x += 1.0f; root->bbox.pmax.y += 1.0f; root->bbox.pmax.z += 1.0f;
     root->bbox.pmin.x -= 1.0f; root->bbox.pmin.y -= 1.0f; root->bbox.pmin.z -= 1.0f;
@@ -85,7 +87,7 @@ int vpt_octree_build(const vpt_gpu_vdb* h_volumes, int n, vpt_devptr_t* d_root_o
     vpt::SceneEntry ent; ent.device = device; ent.n = n;
     ent.root6[0] = root->bbox.pmin.x; ent.root6[1] = root->bbox.pmin.y; ent.root6[2] = root->bbox.pmin.z;
     ent.root6[3] = root->bbox.pmax.x; ent.root6[4] = root->bbox.pmax.y; ent.root6[5] = root->bbox.pmax.z;
-    ent.max_extinction = root->max_extinction; ent.min_extinction = root->min_extinction;
+    ent.max_extinction = root->max_extinction; ent.min_extinction = root->min_extinction; ent.any_flags = any_flags;
     std::vector<int> counts(585);
     std::vector<vpt::OctInternal> internal(vpt::kOctInternalNodes);
     std::vector<uint2> leaf_list(vpt::kOctLeaves);

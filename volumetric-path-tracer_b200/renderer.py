@@ -101,11 +101,19 @@ class Renderer:
     def set_option(self, key, value):
         check(lib.vpt_set_option(self.ctx, key.encode(), int(value)), self.ctx, f"vpt_set_option({key})")
 
+    def set_brick_volume(self, volume):
+        """Fast mode: trace volume 0 from `volume`'s brick pool (None: back to the tex3D parity path)."""
+        if volume is None:
+            check(lib.vpt_set_brick_volume(self.ctx, 0, 0, 0, 0), self.ctx, "vpt_set_brick_volume")
+        else:
+            if not getattr(volume, "brick_pool", 0): volume.build_bricks()
+            check(lib.vpt_set_brick_volume(self.ctx, volume.brick_pool, *volume.dims), self.ctx, "vpt_set_brick_volume")
+
     def counters(self, reset=True):
         out = (C.c_ulonglong * 8)()
         check(lib.vpt_get_counters(self.ctx, out, 1 if reset else 0), self.ctx, "vpt_get_counters")
         v = list(out)
-        return dict(lookups=v[0], lane_steps=v[1], warp_step_iters=v[2], lane_services=v[3], warp_service_rounds=v[4], rays=v[5])
+        return dict(lookups=v[0], lane_steps=v[1], warp_step_iters=v[2], lane_services=v[3], warp_service_rounds=v[4], rays=v[5], brick_fetches=v[6])
 
     def kernel_times(self):
         ms = (C.c_float * 4)(); n = (C.c_int * 4)()

@@ -223,6 +223,45 @@ class Volume:
         return v
 
     @staticmethod
+    def procedural(dims, box_min=None, res=1.0, scale=0.1, seed=123, device="cuda:0", keep_dense=True):
+        """GPU_PROC_VOL::create_volume (gpu_vdb.cpp:508-609) headless: Perlin density grid filled on the device by the library
+        (vpt_procedural_fill: the reference's fill_volume_buffer, noise type 0, zero jitter), turned into the same clamp /
+        linear / normalised 3-D texture, with the VDB_INFO the reference hard-codes for procedural volumes (max 1, min 0,
+        bmax = bmin + dim, xform = scale(res); quirk Q10).  dims = (dx, dy, dz) voxels."""
+        dx, dy, dz = [int(d) for d in dims]
+        v = Volume()
+        torch.cuda.set_device(torch.device(device))
+        dense = torch.empty(dz * dy * dx, dtype=torch.float32, device=device)
+        check(lib.vpt_procedural_fill(C.c_void_p(dense.data_ptr()), dx, dy, dz, 0, float(scale), int(seed), None), None, "vpt_procedural_fill")
+        torch.cuda.synchronize()
+        tex, arr = C.c_uint64(0), C.c_void_p(0)
+        check(lib.vpt_texture_create_3d_from_device(C.c_void_p(dense.data_ptr()), 1, dx, dy, dz, C.byref(tex), C.byref(arr)), None, "vpt_texture_create_3d_from_device")
+        t = Texture(tex.value, arr); v.textures.append(t)
+        if box_min is None: box_min = (-dx * res / 2.0, -dy * res / 2.0, -dz * res / 2.0)
+        info = v.rec.vdb_info
+        info.voxelsize = float(res); info.dim = N.i3(dx, dy, dz)
+        info.bmin = N.f3(*[float(b) for b in box_min]); info.bmax = N.f3(float(box_min[0] + dx), float(box_min[1] + dy), float(box_min[2] + dz))
+        info.max_density = 1.0; info.min_density = 0.0; info.density_texture = t.tex
+        X = mat4_identity()
+        X[0][0] = X[1][1] = X[2][2] = np.float32(res)                     # mat4::scale(res) on the identity
+        for a in range(4):
+            for b in range(4):
+                v.rec.xform[a][b] = float(X[a][b])
+        v.dims = (dx, dy, dz)
+        v.dense = dense if keep_dense else None
+        v.brick_pool = 0
+        return v
+
+    def build_bricks(self):
+        """Brick pool of the density grid for fast mode (vpt_bricks_create); needs the dense device grid kept by procedural()."""
+        assert getattr(self, "dense", None) is not None, "no dense device grid kept for this volume"
+        pool = C.c_uint64(0); nbytes = C.c_ulonglong(0)
+        dx, dy, dz = self.dims
+        check(lib.vpt_bricks_create(C.c_void_p(self.dense.data_ptr()), dx, dy, dz, C.byref(pool), C.byref(nbytes)), None, "vpt_bricks_create")
+        self.brick_pool = pool.value; self.brick_bytes = int(nbytes.value)
+        return self.brick_pool
+
+    @staticmethod
     def load_vdb(path, density="density", emission="heat", color="Cd"):
         got = load_vdb_grid(path, density)
         if got is None:
