@@ -45,8 +45,8 @@ GPU_VDB::~GPU_VDB() {}
 extern "C" void BuildBVH(BVH& bvh, GPU_VDB* volumes, int numVolumes, AABB& sceneBounds, bool debug_bvh);
 extern "C" void build_octree(OCTNode* root, GPU_VDB* volumes, int num_volumes, int depth, bool debug);
 
-static CUmodule g_mod[2] = {nullptr, nullptr};
-static CUfunction g_fn[2] = {nullptr, nullptr};   // [0] unmodified kernel, [1] "nobn" build
+static CUmodule g_mod[3] = {nullptr, nullptr, nullptr};
+static CUfunction g_fn[3] = {nullptr, nullptr, nullptr};   // [0] unmodified kernel, [1] "nobn" build, [2] a candidate drop-in module (level (A) test)
 static CUmodule g_bn_mod = nullptr;
 static CUfunction g_bn_fn = nullptr;
 
@@ -66,10 +66,12 @@ int vptref_sizes(size_t* out, int n) {
     return m;
 }
 
-// which: 0 = unmodified reference kernel, 1 = build with the blue-noise tail compiled out.
+// which: 0 = unmodified reference kernel, 1 = build with the blue-noise tail compiled out, 2 = any other module that claims to be
+// a drop-in: it goes through the very same loader calls and the very same launch below.
 int vptref_load_kernel(const char* cubin_path, int which) {
     CKR(cudaFree(0));
-    if (which < 0 || which > 1) return -1;
+    if (which < 0 || which > 2) return -1;
+    if (g_mod[which]) { cuModuleUnload(g_mod[which]); g_mod[which] = nullptr; g_fn[which] = nullptr; }
     CK(cuModuleLoad(&g_mod[which], cubin_path));
     CK(cuModuleGetFunction(&g_fn[which], g_mod[which], "volume_rt_kernel"));
     return 0;
@@ -106,10 +108,15 @@ int vptref_launch(void** params, unsigned width, unsigned height, int which, int
     return 0;
 }
 
-int vptref_bn_advance(const void* kernel_params, int sync) {
+// n_entries: how many blue-noise entries the pass advances.  The reference updates entry idx = y*W + x from the thread of pixel
+// (x, y) when idx < 65536, i.e. min(W*H, 65536) entries; the generated kernel keeps only the `idx < 65536` guard, so it is launched
+// with exactly that many single-thread blocks.
+int vptref_bn_advance(const void* kernel_params, int sync, unsigned n_entries) {
     if (!g_bn_fn) return -2;
     void* params[] = { (void*)kernel_params };
-    CK(cuLaunchKernel(g_bn_fn, 256, 1, 1, 256, 1, 1, 0, NULL, params, NULL));
+    if (n_entries > 65536u) n_entries = 65536u;
+    if (n_entries == 0) return 0;
+    CK(cuLaunchKernel(g_bn_fn, n_entries, 1, 1, 1, 1, 1, 0, NULL, params, NULL));
     if (sync) CKR(cudaDeviceSynchronize());
     return 0;
 }

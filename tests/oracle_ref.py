@@ -23,7 +23,7 @@ def available():
 
 class RefOracle:
     """Drives the reference kernel with a byte-identical parameter block (LaunchParams.array)."""
-    UNMODIFIED, NOBN = 0, 1
+    UNMODIFIED, NOBN, CANDIDATE = 0, 1, 2
 
     def __init__(self):
         if not available():
@@ -33,7 +33,7 @@ class RefOracle:
         L.vptref_load_kernel.argtypes = [C.c_char_p, C.c_int]; L.vptref_load_kernel.restype = C.c_int
         L.vptref_load_bn_kernel.argtypes = [C.c_char_p]; L.vptref_load_bn_kernel.restype = C.c_int
         L.vptref_launch.argtypes = [C.POINTER(C.c_void_p), C.c_uint, C.c_uint, C.c_int, C.c_int]; L.vptref_launch.restype = C.c_int
-        L.vptref_bn_advance.argtypes = [C.c_void_p, C.c_int]; L.vptref_bn_advance.restype = C.c_int
+        L.vptref_bn_advance.argtypes = [C.c_void_p, C.c_int, C.c_uint]; L.vptref_bn_advance.restype = C.c_int
         L.vptref_build_octree.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]; L.vptref_build_octree.restype = C.c_int
         L.vptref_build_bvh.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_float)]
         L.vptref_build_bvh.restype = C.c_int
@@ -77,6 +77,11 @@ class RefOracle:
         if rc: raise RuntimeError(f"vptref_load_bn_kernel -> {rc}")
         self._loaded = True
 
+    def load_candidate(self, cubin_path):
+        """Load another module through the reference loader sequence (cuModuleLoad + cuModuleGetFunction("volume_rt_kernel"))."""
+        rc = self.lib.vptref_load_kernel(os.fspath(cubin_path).encode(), self.CANDIDATE)
+        if rc: raise RuntimeError(f"vptref_load_kernel({cubin_path}) -> {rc}")
+
     def sizes(self):
         out = (C.c_size_t * 12)(); n = self.lib.vptref_sizes(out, 12)
         return list(out)[:n]
@@ -95,8 +100,9 @@ class RefOracle:
         if rc: raise RuntimeError(f"vptref_launch -> {rc}")
 
     def bn_advance(self, kp, sync=True):
+        """The reference's own update statements for the entries a pass really advances: min(W*H, 65536)."""
         self.load_kernels()
-        rc = self.lib.vptref_bn_advance(C.cast(C.byref(kp), C.c_void_p), 1 if sync else 0)
+        rc = self.lib.vptref_bn_advance(C.cast(C.byref(kp), C.c_void_p), 1 if sync else 0, min(int(kp.resolution.x) * int(kp.resolution.y), 65536))
         if rc: raise RuntimeError(f"vptref_bn_advance -> {rc}")
 
     def render(self, renderer, n_passes, race_free=True):

@@ -298,3 +298,77 @@ def test_two_rank_nccl_gather_is_bitwise_identical():
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     print(out.stdout[-2000:], out.stderr[-2000:])
     assert out.returncode == 0 and "BITWISE_OK" in out.stdout
+
+
+# ---- level (A): the single-entry module behind the reference's unchanged Driver-API loader ------------------------------------
+LEVEL_A = os.path.join(os.path.dirname(V.LIB_PATH), "volume_rt_kernel_b200.cubin")
+
+
+def _launch_candidate(orc, r, passes):
+    for _ in range(passes):                                       # main.cpp:1823-1829: cuLaunchKernel(grid (w/16+1, h/16+1), block (16,16), params[9]); ++iteration; sync
+        orc.launch(r.params.array, r.width, r.height, orc.CANDIDATE)
+        r.kp.iteration += 1
+    torch.cuda.synchronize()
+
+
+@needs_ref
+@pytest.mark.skipif(not os.path.exists(LEVEL_A), reason="volume_rt_kernel_b200.cubin not built")
+@pytest.mark.parametrize("cfg", [
+    dict(W=512, H=512, passes=1, kp=dict(ray_depth=1)),                                    # BASELINE configs[0] resolution (plumbing config)
+    dict(W=256, H=256, passes=3, kp=dict(ray_depth=100), unmodified=True),                 # vs the UNMODIFIED reference kernel at its race-free size
+    dict(W=320, H=200, passes=2, kp=dict(ray_depth=4, volume_depth=5, phase_g1=-0.4)),
+    dict(W=33, H=17, passes=2, kp=dict(ray_depth=2)),                                      # fewer pixels than blue-noise entries, ragged grid
+    dict(W=256, H=160, passes=2, kp=dict(ray_depth=3, volume_depth=2), lights=True, sphere=True),
+    dict(W=256, H=128, passes=2, kp=dict(ray_depth=3), aperture=0.2),                      # thin lens
+    dict(W=200, H=120, passes=2, kp=dict(ray_depth=2), instances=8),                       # leaf lists read from the caller's OCTNodes
+    dict(W=200, H=120, passes=1, kp=dict(ray_depth=6, integrator=1), atmo=True),           # volumetric path integrator, HDRI sky estimator
+    dict(W=200, H=120, passes=1, kp=dict(ray_depth=2, environment_type=0), atmo=True),     # precomputed sky environment
+])
+def test_level_a_module_through_the_reference_loader(dragon, cfg):
+    """The cubin is loaded with the harness's cuModuleLoad + cuModuleGetFunction("volume_rt_kernel") -- the same two calls and the same
+    cuLaunchKernel line that drive the reference kernel -- on the REFERENCE's own pointer-linked octree, and must match the oracle."""
+    if cfg.get("atmo") and not has_atmo: pytest.skip("oracle/_ref/atmo not built")
+    lights = [((9.0, 6.0, 2.0), (1.0, 0.8, 0.6), 40.0), ((-2.0, 3.0, 8.0), (0.5, 0.7, 1.0), 25.0)] if cfg.get("lights") else None
+    inst = scattered(dragon, cfg["instances"], 9, 6.0) if cfg.get("instances") else None
+    scene = make_scene(dragon, lights=lights, instances=inst)
+    if cfg.get("sphere"):
+        sp = scene.h_sphere; sp.center = V.f3(4.0, 6.5, 3.0); sp.radius = 1.2; sp.roughness = 0.7; sp.color = V.f3(0.8, 0.6, 0.3)
+        scene.d_sphere.copy_(torch.frombuffer(bytearray(bytes(sp)), dtype=torch.uint8))
+    orc = oracle_ref.RefOracle()
+    if cfg.get("atmo"): orc.atmosphere_init(scene.atmos)
+    orc.load_kernels(); orc.load_candidate(LEVEL_A)
+    W, H, P = cfg["W"], cfg["H"], cfg["passes"]
+    cam = scene.frame_camera(W, H, aperture=cfg.get("aperture", 0.0))
+    a = V.Renderer(scene, W, H, kp=make_kp(**cfg["kp"]), cam=cam); ref = V.Renderer(scene, W, H, kp=make_kp(**cfg["kp"]), cam=cam)
+    root = orc.build_octree(scene.h_volumes, len(scene.instances))
+    a.params.p_oct.value = root; ref.params.p_oct.value = root
+    scene.reset_blue_noise(); orc.render(ref, P, race_free=not cfg.get("unmodified")); bn_ref = scene.d_blue_noise.clone()
+    scene.reset_blue_noise(); _launch_candidate(orc, a, P)
+    want = ref.buffers.accum.cpu().numpy(); got = a.buffers.accum.cpu().numpy()
+    frac = flipped_fraction(got, want)
+    print(f"level A {cfg}: flipped {frac:.3g}, max |d| {np.abs(got - want).max():.3g}, ref mean {want.mean():.6g}")
+    assert float(want.mean()) > 1e-4 and frac <= MAX_FLIPPED
+    assert flipped_fraction(a.buffers.depth.cpu().numpy()[:, None], ref.buffers.depth.cpu().numpy()[:, None]) <= MAX_FLIPPED
+    assert torch.equal(scene.d_blue_noise, bn_ref), "blue-noise state after the passes"
+    assert float(a.buffers.cost.abs().max()) == 0.0
+    dm = a.buffers.display.cpu().numpy().view(np.uint8).reshape(-1, 4).astype(int)
+    dr = ref.buffers.display.cpu().numpy().view(np.uint8).reshape(-1, 4).astype(int)
+    assert np.abs(dm - dr).max() <= 1
+    assert a.kp.iteration == ref.kp.iteration == P
+
+
+@needs_ref
+@pytest.mark.skipif(not os.path.exists(LEVEL_A), reason="volume_rt_kernel_b200.cubin not built")
+def test_level_a_non_sampling_passes(dragon):
+    """iteration >= max_interactions: buffers are only re-tonemapped; render == false: WHITE into the accumulator (:2248-2287)."""
+    scene = make_scene(dragon)
+    orc = oracle_ref.RefOracle(); orc.load_kernels(); orc.load_candidate(LEVEL_A)
+    a = V.Renderer(scene, 128, 64, kp=make_kp(ray_depth=1, max_interactions=2))
+    a.params.p_oct.value = orc.build_octree(scene.h_volumes, 1)
+    _launch_candidate(orc, a, 2); acc2 = a.buffers.accum.clone()
+    _launch_candidate(orc, a, 2)
+    assert torch.equal(acc2, a.buffers.accum)
+    b = V.Renderer(scene, 128, 64, kp=make_kp(ray_depth=1, render=0), cam=a.cam)
+    b.params.p_oct.value = a.params.p_oct.value
+    _launch_candidate(orc, b, 1)
+    assert torch.equal(b.buffers.accum, torch.ones_like(b.buffers.accum))

@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
-echo "== pytest gpu"; timeout 1500 python -X faulthandler -m pytest tests -m gpu -q -x 2>&1 | tail -25
+echo "== pytest gpu"; timeout 1500 python -X faulthandler -m pytest tests -m gpu -q 2>&1 | tail -40
 echo "== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3
 echo "== bench ours"; timeout 900 python bench.py --steps 10 --warmup 3 2>gpurun_out/bench_ours.err | tail -1 | tee gpurun_out/r02a_bench_ours.json | cut -c1-2500; tail -3 gpurun_out/bench_ours.err
 echo "== bench reference"; timeout 900 python bench.py --impl reference --steps 3 --warmup 3 2>&1 | tail -1 | tee gpurun_out/r02a_bench_ref.json | cut -c1-300

@@ -16,7 +16,12 @@ $NVCC $ARCH -O2 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off -x cu -c "$HERE/ho
 g++ -O2 -std=c++17 -fPIC -c "$HERE/host/vdb_reader.cpp" -o "$HERE/_obj/vdb_reader.o"
 g++ -O2 -std=c++17 -fPIC -c "$HERE/host/image_io.cpp" -o "$HERE/_obj/image_io.o"
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -c "$HERE/host/sky_table.cpp" -o "$HERE/_obj/sky_table.o"
+# level (A): the single-entry module for the reference's unchanged Driver-API loader (cuModuleLoad -> "volume_rt_kernel")
+$NVCC $ARCH -cubin -O3 --use_fast_math -lineinfo -std=c++17 -DVPT_LEVEL_A_MODULE "$HERE/device/vpt_level_a.cu" -o "$OUT/.volume_rt_kernel_b200.cubin.tmp"
+mv -f "$OUT/.volume_rt_kernel_b200.cubin.tmp" "$OUT/volume_rt_kernel_b200.cubin"
 LIBNAME="${VPT_LIB_NAME:-libvpt_b200.so}"
 $NVCC $ARCH -O2 -std=c++17 -Xcompiler -fPIC -x cu -c "$HERE/host/vpt_comm.cpp" -o "$HERE/_obj/vpt_comm.o"
-$NVCC $ARCH -shared -o "$OUT/$LIBNAME" "$HERE"/_obj/*.o -lz -ldl
+# link under a temporary name and rename: a snapshot (gpurun) taken during the build never sees a half-written library
+$NVCC $ARCH -shared -o "$OUT/.$LIBNAME.tmp" "$HERE"/_obj/*.o -lz -ldl
+mv -f "$OUT/.$LIBNAME.tmp" "$OUT/$LIBNAME"
 echo "built $OUT/$LIBNAME"

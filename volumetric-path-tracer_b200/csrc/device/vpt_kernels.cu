@@ -14,61 +14,13 @@
 //
 // Numerics: compiled with the reference's flags (--use_fast_math); decision-relevant expressions keep the reference
 // build's operation order (read off its SASS) so a pixel's path is reproduced sample for sample (see vpt_math.cuh).
-#include <type_traits>
-#include <cstring>
-#include "vpt_walk.cuh"
-#include "vpt_atmosphere.cuh"
-#include "vpt_kernels.h"
+#include "vpt_frame.cuh"
 
 namespace vpt {
-
-constexpr uint32_t kMissSentinel = 0xffffffffu;   // planeA.w bit pattern marking a miss sample (a NaN no arithmetic produces)
 
 // =====================================================================================================
 // k_prepare_scene
 // =====================================================================================================
-__device__ __forceinline__ const vpt_octnode* oct_ptr(vpt_devptr_t p) { return reinterpret_cast<const vpt_octnode*>(p); }
-
-// per-volume world->index affine, evaluated with the reference's own adjugate formula order
-__device__ VolumeRec make_volume_rec(const vpt_gpu_vdb& g)
-{
-    // n_rc of the transposed matrix == xform[r-1][c-1] in memory order
-    const float n11 = g.xform[0][0], n12 = g.xform[0][1], n13 = g.xform[0][2], n14 = g.xform[0][3];
-    const float n21 = g.xform[1][0], n22 = g.xform[1][1], n23 = g.xform[1][2], n24 = g.xform[1][3];
-    const float n31 = g.xform[2][0], n32 = g.xform[2][1], n33 = g.xform[2][2], n34 = g.xform[2][3];
-    const float n41 = g.xform[3][0], n42 = g.xform[3][1], n43 = g.xform[3][2], n44 = g.xform[3][3];
-
-    const float t11 = n23 * n34 * n42 - n24 * n33 * n42 + n24 * n32 * n43 - n22 * n34 * n43 - n23 * n32 * n44 + n22 * n33 * n44;
-    const float t12 = n14 * n33 * n42 - n13 * n34 * n42 - n14 * n32 * n43 + n12 * n34 * n43 + n13 * n32 * n44 - n12 * n33 * n44;
-    const float t13 = n13 * n24 * n42 - n14 * n23 * n42 + n14 * n22 * n43 - n12 * n24 * n43 - n13 * n22 * n44 + n12 * n23 * n44;
-    const float t14 = n14 * n23 * n32 - n13 * n24 * n32 - n14 * n22 * n33 + n12 * n24 * n33 + n13 * n22 * n34 - n12 * n23 * n34;
-
-    const float det = n11 * t11 + n21 * t12 + n31 * t13 + n41 * t14;
-    const float idet = 1.0f / det;
-
-    // second and third output rows of the inverse (unscaled adjugate entries)
-    const float a01 = n24 * n33 * n41 - n23 * n34 * n41 - n24 * n31 * n43 + n21 * n34 * n43 + n23 * n31 * n44 - n21 * n33 * n44;
-    const float a11 = n13 * n34 * n41 - n14 * n33 * n41 + n14 * n31 * n43 - n11 * n34 * n43 - n13 * n31 * n44 + n11 * n33 * n44;
-    const float a21 = n14 * n23 * n41 - n13 * n24 * n41 - n14 * n21 * n43 + n11 * n24 * n43 + n13 * n21 * n44 - n11 * n23 * n44;
-    const float a31 = n13 * n24 * n31 - n14 * n23 * n31 + n14 * n21 * n33 - n11 * n24 * n33 - n13 * n21 * n34 + n11 * n23 * n34;
-
-    const float a02 = n22 * n34 * n41 - n24 * n32 * n41 + n24 * n31 * n42 - n21 * n34 * n42 - n22 * n31 * n44 + n21 * n32 * n44;
-    const float a12 = n14 * n32 * n41 - n12 * n34 * n41 - n14 * n31 * n42 + n11 * n34 * n42 + n12 * n31 * n44 - n11 * n32 * n44;
-    const float a22 = n12 * n24 * n41 - n14 * n22 * n41 + n14 * n21 * n42 - n11 * n24 * n42 - n12 * n21 * n44 + n11 * n22 * n44;
-    const float a32 = n14 * n22 * n31 - n12 * n24 * n31 - n14 * n21 * n32 + n11 * n24 * n32 + n12 * n21 * n34 - n11 * n22 * n34;
-
-    VolumeRec r;
-    r.m[0][0] = t11 * idet; r.m[0][1] = t12 * idet; r.m[0][2] = t13 * idet; r.adj3[0] = t14;
-    r.m[1][0] = a01 * idet; r.m[1][1] = a11 * idet; r.m[1][2] = a21 * idet; r.adj3[1] = a31;
-    r.m[2][0] = a02 * idet; r.m[2][1] = a12 * idet; r.m[2][2] = a22 * idet; r.adj3[2] = a32;
-    r.idet = idet;
-    r.bmin[0] = g.vdb_info.bmin.x; r.bmin[1] = g.vdb_info.bmin.y; r.bmin[2] = g.vdb_info.bmin.z;
-    r.rdim[0] = 1.0f / float(g.vdb_info.dim.x); r.rdim[1] = 1.0f / float(g.vdb_info.dim.y); r.rdim[2] = 1.0f / float(g.vdb_info.dim.z);
-    r.flags = (g.vdb_info.has_color ? 1u : 0u) | (g.vdb_info.has_emission ? 2u : 0u);
-    r.density_tex = g.vdb_info.density_texture; r.emission_tex = g.vdb_info.emission_texture; r.color_tex = g.vdb_info.color_texture;
-    return r;
-}
-
 // root == nullptr: the octree was built by vpt_octree_build, its flat tables already exist (`hdr` names them, any number of
 // instances) and only the per-volume records -- which depend on the GPU_VDB[] array handed in at render time -- are made here.
 // One kernel for both cases on purpose: the record arithmetic is then the very same machine code.
@@ -89,6 +41,7 @@ __global__ void k_prepare_scene(const vpt_gpu_vdb* __restrict__ vols, const vpt_
         out->num_volumes = N;
         out->single_volume = (N == 1) ? 1 : 0;
         out->internal = internal; out->leaf_list = leaf_list; out->leaf_indices = leaf_indices; out->volumes = vrec;
+        out->leaf_nodes = nullptr;
     }
 
     // internal nodes: 0 = root, 1..8 = level 1, 9..72 = level 2
@@ -135,59 +88,6 @@ __global__ void k_prepare_scene(const vpt_gpu_vdb* __restrict__ vols, const vpt_
 
     // per-volume world->index affine
     for (int v = tid; v < N && v < max_volumes; v += nthreads) vrec[v] = make_volume_rec(vols[v]);
-}
-
-// =====================================================================================================
-// shared helpers of the per-frame kernels
-// =====================================================================================================
-struct FrameShared {
-    SceneTables sc;
-    OctShared   oct;
-    VolumeRec   vol0;      // volume 0 staged for single-volume scenes (the headline case)
-};
-
-VPT_DEV void load_frame_shared(FrameShared& fs, const SceneTables* sc_dev) {
-    if (threadIdx.x == 0 && threadIdx.y == 0) fs.sc = *sc_dev;
-    __syncthreads();
-    // stage_octree assumes a 1-D thread index
-    const int t = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
-    const uint4* src = reinterpret_cast<const uint4*>(fs.sc.internal);
-    uint4* d = reinterpret_cast<uint4*>(fs.oct.node);
-    for (int i = t; i < kOctInternalNodes * 3; i += nt) d[i] = __ldg(src + i);
-    {   // 96-byte record of volume 0
-        const uint4* vs = reinterpret_cast<const uint4*>(fs.sc.volumes);
-        uint4* vd = reinterpret_cast<uint4*>(&fs.vol0);
-        for (int i = t; i < (int)(sizeof(VolumeRec) / 16); i += nt) vd[i] = __ldg(vs + i);
-    }
-    __syncthreads();
-}
-
-VPT_DEV SphereRec load_sphere(const vpt_sphere* s) {
-    SphereRec r;
-    r.center = f3(s->center.x, s->center.y, s->center.z); r.radius = s->radius;
-    r.color = f3(s->color.x, s->color.y, s->color.z); r.roughness = s->roughness;
-    return r;
-}
-
-VPT_DEV float3 ld3(const vpt_f3& v) { return f3(v.x, v.y, v.z); }
-
-// global row of a local row under the interleaved-stripe partition (identity for one rank)
-VPT_DEV int global_row(const FrameGeom& g, int lr) {
-    const int s = lr / g.stripe_h;
-    return (s * g.n_ranks + g.rank) * g.stripe_h + (lr - s * g.stripe_h);
-}
-
-// radical inverse of int(xi*100) in `BASE` (reference vanDerCorput, gpu_vdb/camera.h:49-62)
-template <int BASE>
-VPT_DEV float van_der_corput(Rng& rng) {
-    int n = int(rng.next() * 100);
-    float rand_int = 0, denom = 1, invBase = 1.f / BASE;
-    while (n) {
-        denom *= BASE;
-        rand_int = padd(rand_int, __fdividef((float)(n % BASE), denom));
-        n *= invBase;
-    }
-    return rand_int;
 }
 
 // =====================================================================================================
@@ -328,22 +228,10 @@ k_generate(const FrameArgs fa)
     }   // pass loop
 }
 
-#include "vpt_trace.cuh"
-#include "vpt_trace_brick.cuh"
 
 // =====================================================================================================
 // k_resolve
 // =====================================================================================================
-VPT_DEV float3 aces_fit(float3 v) {                           // reference rtt_and_odt_fit, :2208-2213
-    float3 a = v * (v + f3(0.0245786f)) - f3(0.000090537f);
-    float3 b = v * (0.983729f * v + f3(0.4329510f)) + f3(0.238081f);
-    return a / b;
-}
-
-VPT_DEV float3 mat3_mul(const float m[9], float3 v) {
-    return f3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
-}
-
 // kSky 1: direct integrator with environment_type == 0 (Bruneton sky lookup, `atmo` is the caller's AtmosphereParameters);
 // kSky 2: volumetric path integrator, which always ends on the sky (:1752); kSky 0: HDRI environment -- that variant
 // takes a 16-byte dummy so it keeps its small parameter block and register budget.
@@ -443,11 +331,17 @@ k_resolve(const FrameArgs fa, const typename std::conditional<kSky != 0, vpt_atm
 // =====================================================================================================
 // Per-chunk jitter table: table[p][i] = (x, y) of blue-noise entry i after p advances, p = 0..np-1; the buffer
 // itself is left advanced by `np` passes.  One launch replaces the per-thread replay in k_generate.
-__global__ void k_bn_prepare(float3* bn, float2* table, int np)
+// `limit` = min(W*H, 65536): the reference advances entry idx = y*W + x from the thread of pixel (x, y), so a frame of fewer than
+// 65536 pixels leaves the entries beyond W*H untouched (they are still READ as jitter through (y % 256) * 256 + x % 256).
+__global__ void k_bn_prepare(float3* bn, float2* table, int np, int limit)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 256 * 256) return;
     float3 val = bn[idx];
+    if (idx >= limit) {
+        for (int i = 0; i < np; ++i) table[(size_t)i * 65536 + idx] = make_float2(val.x, val.y);
+        return;
+    }
     for (int i = 0; i < np; ++i) {
         table[(size_t)i * 65536 + idx] = make_float2(val.x, val.y);
         val.x += (1.0f + sqrtf(5.0f)) / 2.0f; val.y += (1.0f + sqrtf(5.0f)) / 2.0f; val.z += (1.0f + sqrtf(5.0f)) / 2.0f;
@@ -456,10 +350,10 @@ __global__ void k_bn_prepare(float3* bn, float2* table, int np)
     bn[idx] = val;
 }
 
-__global__ void k_bn_advance(float3* bn, int n)
+__global__ void k_bn_advance(float3* bn, int n, int limit)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= 256 * 256) return;
+    if (idx >= 256 * 256 || idx >= limit) return;
     float3 val = bn[idx];
     for (int i = 0; i < n; ++i) {
         val.x += (1.0f + sqrtf(5.0f)) / 2.0f; val.y += (1.0f + sqrtf(5.0f)) / 2.0f; val.z += (1.0f + sqrtf(5.0f)) / 2.0f;
@@ -571,15 +465,15 @@ cudaError_t launch_resolve(const FrameArgs& fa, const vpt_atmosphere* sky, int n
     return cudaGetLastError();
 }
 
-cudaError_t launch_bn_prepare(void* bn, float2* table, int np, cudaStream_t s)
+cudaError_t launch_bn_prepare(void* bn, float2* table, int np, int limit, cudaStream_t s)
 {
-    k_bn_prepare<<<256, 256, 0, s>>>(reinterpret_cast<float3*>(bn), table, np);
+    k_bn_prepare<<<256, 256, 0, s>>>(reinterpret_cast<float3*>(bn), table, np, limit);
     return cudaGetLastError();
 }
 
-cudaError_t launch_bn_advance(void* bn, int n, cudaStream_t s)
+cudaError_t launch_bn_advance(void* bn, int n, int limit, cudaStream_t s)
 {
-    k_bn_advance<<<256, 256, 0, s>>>(reinterpret_cast<float3*>(bn), n);
+    k_bn_advance<<<256, 256, 0, s>>>(reinterpret_cast<float3*>(bn), n, limit);
     return cudaGetLastError();
 }
 

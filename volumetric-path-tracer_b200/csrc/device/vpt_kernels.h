@@ -61,8 +61,9 @@ cudaError_t launch_fill_perlin(float* d_buffer, int dx, int dy, int dz, float sc
 cudaError_t launch_build_bricks(const float* d_dense, int dx, int dy, int dz, float* d_bricks, cudaStream_t s);
 // sky != null selects the environment_type == 0 variant (host copy of the caller's AtmosphereParameters)
 cudaError_t launch_resolve(const FrameArgs& fa, const vpt_atmosphere* sky, int n_passes, int sampled, int write_display, cudaStream_t s);
-cudaError_t launch_bn_prepare(void* bn, float2* table, int np, cudaStream_t s);
-cudaError_t launch_bn_advance(void* bn, int n, cudaStream_t s);
+// limit = min(W*H, 65536) entries are advanced (the reference updates entry y*W + x from pixel (x, y))
+cudaError_t launch_bn_prepare(void* bn, float2* table, int np, int limit, cudaStream_t s);
+cudaError_t launch_bn_advance(void* bn, int n, int limit, cudaStream_t s);
 cudaError_t launch_unpermute(const void* gathered, void* full, const FrameGeom& g, int elem_bytes, cudaStream_t s);
 
 } // namespace vpt

@@ -45,6 +45,9 @@ struct SceneTables {
     const uint2*       leaf_list;           // [512] (offset, count) into leaf_indices
     const int*         leaf_indices;
     const VolumeRec*   volumes;             // [num_volumes]
+    // level (A) entry only (vpt_level_a.cu): leaves read straight from the caller's pointer-linked OCTNodes, no flat lists.
+    // Null everywhere else.  [512] pointers to the leaf nodes (null where the leaf does not exist).
+    const void* const* leaf_nodes;
 };
 
 } // namespace vpt

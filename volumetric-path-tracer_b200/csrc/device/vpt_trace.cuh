@@ -160,7 +160,7 @@ VPT_DEV void store_walk(const PoolView& pv, int s, const PathState& st)
 // of that instantiation (smaller hot loop: the kernel is fetch-stall bound)
 template <bool kLean>
 VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph, uint32_t& nlook,
-                       const PoolView& pv, int slot)
+                       float* beta, int beta_stride)      // the path's throughput: x, y, z at beta[0], beta[stride], beta[2 * stride]
 {
     const SceneTables& sc = fs.sc;
     const vpt_kernel_params& kp = fa.kp;
@@ -199,9 +199,9 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
             const float3 Cd = kLean ? fmax3(f3(0.0f), volume_color(fs.vol0, st.wpos)) : leaf_color(sc, fs.vol0, leaf, st.wpos);
             const int index = int(floorf(fminf(fmaxf((density * tc.inv_max * 255.0f / kp.emission_pivot), 0.0f), 255.0f)));
             const float3 density_color = reinterpret_cast<const float3*>(kp.density_color_texture)[index];
-            float3 beta = f3(pv.f(9, slot), pv.f(10, slot), pv.f(11, slot));     // the path's throughput lives in the parked record
-            beta *= (ld3(kp.albedo) * Cd * density_color / ld3(kp.extinction)) * float(kp.energy_inject);
-            pv.f(9, slot) = beta.x; pv.f(10, slot) = beta.y; pv.f(11, slot) = beta.z;
+            float3 b3 = f3(beta[0], beta[beta_stride], beta[2 * beta_stride]);     // in k_trace the throughput lives in the parked record
+            b3 *= (ld3(kp.albedo) * Cd * density_color / ld3(kp.extinction)) * float(kp.energy_inject);
+            beta[0] = b3.x; beta[beta_stride] = b3.y; beta[2 * beta_stride] = b3.z;
             st.op = OP_GLUE; st.exit_reason = EX_SCATTER;
         }
     } else {
@@ -537,7 +537,7 @@ k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atm
                     break;
                 }
                 if (cur >= 0) {
-                    walk_step<kLean>(st, fs, fa, tc, sph, nlook, pv, cur); lane_steps++;
+                    walk_step<kLean>(st, fs, fa, tc, sph, nlook, &pv.f(9, cur), kPool); lane_steps++;
                     if (st.op != OP_STEP) {                        // walk ended: park the ray with its new tag
                         store_walk(pv, cur, st);
                         if (cur == 0) tag0 = st.op; else if (cur == 1) tag1 = st.op; else tag2 = st.op;

@@ -196,27 +196,41 @@ VPT_DEV float3 volume_emission(const VolumeRec& v, float3 p, const float3* lut, 
     return lut[int(index)] * scale;
 }
 
+// Leaf volume list: the flat CSR tables, or (level (A) entry) the caller's own OCTNode leaf.
+struct LeafList { const int* idx; uint32_t n; };
+VPT_DEV LeafList leaf_list_of(const SceneTables& sc, int leaf) {
+    LeafList l;
+    if (sc.leaf_nodes) {
+        const vpt_octnode* nd = reinterpret_cast<const vpt_octnode*>(sc.leaf_nodes[leaf]);
+        l.idx = nd ? nd->vol_indices : nullptr; l.n = nd ? (uint32_t)nd->num_volumes : 0u;
+    } else {
+        const uint2 lst = sc.leaf_list[leaf];
+        l.idx = sc.leaf_indices + lst.x; l.n = lst.y;
+    }
+    return l;
+}
+
 VPT_DEV float leaf_density(const SceneTables& sc, const VolumeRec& vol0, int leaf, float3 p) {
     if (sc.single_volume) return 0.0f + volume_density(vol0, p);
-    const uint2 lst = sc.leaf_list[leaf];
+    const LeafList lst = leaf_list_of(sc, leaf);
     float density = 0.0f;
-    for (uint32_t i = 0; i < lst.y; ++i) density += volume_density(sc.volumes[sc.leaf_indices[lst.x + i]], p);
+    for (uint32_t i = 0; i < lst.n; ++i) density += volume_density(sc.volumes[lst.idx[i]], p);
     return density;
 }
 
 VPT_DEV float3 leaf_color(const SceneTables& sc, const VolumeRec& vol0, int leaf, float3 p) {
     if (sc.single_volume) return fmax3(f3(0.0f), volume_color(vol0, p));
-    const uint2 lst = sc.leaf_list[leaf];
+    const LeafList lst = leaf_list_of(sc, leaf);
     float3 color = f3(0.0f);
-    for (uint32_t i = 0; i < lst.y; ++i) color = fmax3(color, volume_color(sc.volumes[sc.leaf_indices[lst.x + i]], p));
+    for (uint32_t i = 0; i < lst.n; ++i) color = fmax3(color, volume_color(sc.volumes[lst.idx[i]], p));
     return color;
 }
 
 VPT_DEV float3 leaf_emission(const SceneTables& sc, const VolumeRec& vol0, int leaf, float3 p, const float3* lut, float pivot, float scale) {
     if (sc.single_volume) return f3(0.0f) + volume_emission(vol0, p, lut, pivot, scale);
-    const uint2 lst = sc.leaf_list[leaf];
+    const LeafList lst = leaf_list_of(sc, leaf);
     float3 e = f3(0.0f);
-    for (uint32_t i = 0; i < lst.y; ++i) e += volume_emission(sc.volumes[sc.leaf_indices[lst.x + i]], p, lut, pivot, scale);
+    for (uint32_t i = 0; i < lst.n; ++i) e += volume_emission(sc.volumes[lst.idx[i]], p, lut, pivot, scale);
     return e;
 }
 

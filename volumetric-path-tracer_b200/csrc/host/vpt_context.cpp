@@ -237,7 +237,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
                 for (int a = 0; a < 3; ++a) { hdr.root_pmin[a] = ent.root6[a]; hdr.root_pmax[a] = ent.root6[3 + a]; }
                 hdr.max_extinction = ent.max_extinction; hdr.min_extinction = ent.min_extinction;
                 hdr.num_volumes = ent.n; hdr.single_volume = ent.n == 1 ? 1 : 0;
-                hdr.internal = ent.d_internal; hdr.leaf_list = ent.d_leaf_list; hdr.leaf_indices = ent.d_leaf_indices; hdr.volumes = c->d_vrec;
+                hdr.internal = ent.d_internal; hdr.leaf_list = ent.d_leaf_list; hdr.leaf_indices = ent.d_leaf_indices; hdr.volumes = c->d_vrec; hdr.leaf_nodes = nullptr;
                 VPT_CUDA(c, vpt::launch_prepare_volumes(reinterpret_cast<const vpt_gpu_vdb*>(d_volumes), hdr, c->d_scene, c->d_vrec, stream));
                 c->scene_single_volume = ent.n == 1;
             } else {
@@ -325,12 +325,14 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         return e;
     };
     const uint32_t it0 = kp.iteration;
+    const unsigned long long frame_px = (unsigned long long)kp.resolution.x * kp.resolution.y;
+    const int bn_limit = frame_px < 65536ull ? (int)frame_px : 65536;
     unsigned done = 0;
     while (done < n_sampled) {
         const unsigned np = (n_sampled - done) < (unsigned)chunk ? (n_sampled - done) : (unsigned)chunk;
         fa.kp.iteration = it0 + done;
         VPT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned) * 2, stream));
-        VPT_CUDA(c, timed(3, [&] { return vpt::launch_bn_prepare((void*)kp.blue_noise_buffer, c->d_bn_table, (int)np, stream); }));   // jitter table + advance
+        VPT_CUDA(c, timed(3, [&] { return vpt::launch_bn_prepare((void*)kp.blue_noise_buffer, c->d_bn_table, (int)np, bn_limit, stream); }));   // jitter table + advance
         VPT_CUDA(c, timed(0, [&] { return vpt::launch_generate(fa, (int)np, stream); }));
         if (c->brick_pool) VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace_brick(fa, c->brick_pool, c->brick_dims, trace_ctas, stream); }));
         else VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, vol_integ ? &atmo : nullptr, lean, trace_ctas, stream); }));
@@ -345,7 +347,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         fa.kp.iteration = it0 + n_sampled;
         if (c->gather_pending) { int rc = vpt::comm_before_accum_write(c, stream); if (rc != VPT_OK) return rc; }
         VPT_CUDA(c, vpt::launch_resolve(fa, sky, (int)(n_passes - n_sampled), 0, 1, stream));
-        VPT_CUDA(c, vpt::launch_bn_advance((void*)kp.blue_noise_buffer, (int)(n_passes - n_sampled), stream));
+        VPT_CUDA(c, vpt::launch_bn_advance((void*)kp.blue_noise_buffer, (int)(n_passes - n_sampled), bn_limit, stream));
         c->launches += 2;
     }
     // multi-GPU: the one collective of the path -- all-gather of the rank-local frame into the caller's full-frame buffers
