@@ -136,6 +136,10 @@ int  vpt_procedural_fill(float* d_buffer, int dim_x, int dim_y, int dim_z, int n
  * VPT_ERR_UNSUPPORTED.  d_pool = 0 returns the context to parity mode (tex3D). */
 int  vpt_bricks_create(const float* d_dense, int dim_x, int dim_y, int dim_z, vpt_devptr_t* d_pool_out, unsigned long long* bytes_out);
 int  vpt_bricks_read(vpt_devptr_t d_pool, unsigned long long first_brick, unsigned long long n_bricks, float* h_out);   /* 128 floats per brick */
+/* Diagnostic: the software filter under three weight rules (m = 0 rounded to 1/256 -- the production rule --, 1 truncated to 1/256, 2 full
+ * fp32 fraction), reading the bricks from global memory, against tex3D on n pseudo-random points: out12[m*4 + 0..3] = max |d|, sum |d|,
+ * number of bit-identical results, n. */
+int  vpt_debug_sampler_compare(vpt_tex_t tex, vpt_devptr_t d_pool, int dim_x, int dim_y, int dim_z, int n_points, unsigned seed, double out12[12]);
 int  vpt_bricks_destroy(vpt_devptr_t d_pool);
 int  vpt_set_brick_volume(vpt_context* ctx, vpt_devptr_t d_pool, int dim_x, int dim_y, int dim_z);
 

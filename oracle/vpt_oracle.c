@@ -547,9 +547,12 @@ int orc_render_pass(const orc_scene* s, const vpt_camera* cam, const vpt_kernel_
     return 0;
 }
 
-void orc_bn_advance(float* bn) {                                                    /* render_kernel.cu:2319-2325 */
+/* render_kernel.cu:2319-2325: the thread of pixel idx = y*W + x advances entry idx when idx < 65536, so a pass advances the first
+ * min(W*H, 65536) entries */
+void orc_bn_advance(float* bn, int n_entries) {
     const float g = (1.0f + sqrtf(5.0f)) / 2.0f;
-    for (int i = 0; i < 256 * 256 * 3; ++i) bn[i] = fmodf(bn[i] + g, 1.0f);
+    if (n_entries > 256 * 256) n_entries = 256 * 256;
+    for (int i = 0; i < n_entries * 3; ++i) bn[i] = fmodf(bn[i] + g, 1.0f);
 }
 
 size_t orc_sizeof_scene(void) { return sizeof(orc_scene); }

@@ -49,7 +49,7 @@ class CpuOracle:
         self.lib.orc_render_pass.argtypes = [C.POINTER(OrcScene), C.POINTER(N.camera), C.POINTER(N.Kernel_params), C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
         self.lib.orc_render_pass.restype = C.c_int
-        self.lib.orc_bn_advance.argtypes = [C.POINTER(C.c_float)]
+        self.lib.orc_bn_advance.argtypes = [C.POINTER(C.c_float), C.c_int]
         self.lib.orc_sizeof_scene.restype = C.c_size_t; self.lib.orc_sizeof_volume.restype = C.c_size_t
         assert self.lib.orc_sizeof_scene() == C.sizeof(OrcScene) and self.lib.orc_sizeof_volume() == C.sizeof(OrcVolume), "oracle struct layout drifted"
         self._keep = []
@@ -105,7 +105,7 @@ class CpuOracle:
             rc = self.lib.orc_render_pass(C.byref(self.scene), C.byref(cam), C.byref(k), x0, y0, x1, y1, _fp(accum), _fp(depth), _fp(raw),
                                           disp.ctypes.data_as(C.POINTER(C.c_uint32)), _fp(self.bn))
             if rc: raise RuntimeError(f"orc_render_pass -> {rc}")
-            self.lib.orc_bn_advance(_fp(self.bn))
+            self.lib.orc_bn_advance(_fp(self.bn), min(W * H, 65536))
             k.iteration += 1
         return (accum, depth, raw, disp) if want_aux else accum
 

@@ -43,7 +43,9 @@ def test_procedural_fill_against_reference_fill_kernel():
     vol = V.Volume.procedural(dims, scale=0.1, seed=123)
     ref = torch.full((dims[0] * dims[1] * dims[2],), -7.0, dtype=torch.float32, device="cuda")
     oracle_ref.RefOracle().fill_volume(ref.data_ptr(), dims, scale=0.1, noise_type=0)
+    torch.cuda.synchronize()
     a = vol.dense.cpu().numpy(); b = ref.cpu().numpy()
+    print(f"reference fill: {int((b == -7.0).sum())} of {b.size} voxels untouched, finite {bool(np.isfinite(b).all())}, range [{np.nanmin(b):.3g}, {np.nanmax(b):.3g}]")
     assert np.isfinite(a).all() and a.min() < -0.3 and a.max() > 0.3, "Perlin noise spans negative and positive densities (quirk Q10)"
     print(f"fill: max |ours - reference| = {np.abs(a - b).max():.3g} (jitter bound ~ {0.1 / min(dims) * 2:.3g}), corr {np.corrcoef(a, b)[0, 1]:.6f}")
     assert np.abs(a - b).max() < 2e-3
@@ -68,6 +70,20 @@ def test_brick_pool_layout(perlin):
         got = pool[bz, by, bx]
         assert np.array_equal(got[:125], want)
         assert got[125] == want.max() and got[126] == want.min() and got[127] == 0.0
+
+
+def test_software_filter_against_texture_unit(perlin):
+    """The brick sampler's blend against tex3D on a million random points, for the three candidate weight rules (rounded / truncated
+    to 1/256, full fp32).  The production rule must stay within the texture unit's own quantisation step."""
+    out = (C.c_double * 12)()
+    tex = perlin.rec.vdb_info.density_texture
+    V._native.check(V.lib.vpt_debug_sampler_compare(tex, perlin.brick_pool, *perlin.dims, 1 << 20, 7, out), None, "vpt_debug_sampler_compare")
+    names = ("weights rounded to 1/256", "weights truncated to 1/256", "full fp32 weights")
+    for m in range(3):
+        mx, sm, same, n = out[4 * m:4 * m + 4]
+        print(f"software filter vs tex3D, {names[m]}: max |d| {mx:.3g}, mean |d| {sm / n:.3g}, bit-identical {100 * same / n:.2f} %")
+    prod = 0
+    assert out[4 * prod] < 5e-3 and out[4 * prod + 1] / out[4 * prod + 3] < 5e-4
 
 
 @needs_ref

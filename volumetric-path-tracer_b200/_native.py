@@ -154,7 +154,7 @@ EXPORTED_SYMBOLS = [
     "vpt_env_tables_create", "vpt_ins_load", "vpt_env_sky_tabulate",
     "vpt_octree_info", "vpt_octree_read_flat", "vpt_bvh_build", "vpt_bvh_read", "vpt_bvh_destroy", "vpt_env_tables_compute",
     "vpt_comm_get_unique_id", "vpt_comm_init", "vpt_comm_set_gather", "vpt_comm_wait", "vpt_comm_info", "vpt_comm_destroy",
-    "vpt_texture_create_3d_from_device", "vpt_procedural_fill", "vpt_bricks_create", "vpt_bricks_destroy", "vpt_set_brick_volume", "vpt_bricks_read",
+    "vpt_texture_create_3d_from_device", "vpt_procedural_fill", "vpt_bricks_create", "vpt_bricks_destroy", "vpt_set_brick_volume", "vpt_bricks_read", "vpt_debug_sampler_compare",
 ]
 
 # ---- prototypes ------------------------------------------------------------------------------------
@@ -200,6 +200,8 @@ lib.vpt_texture_create_3d_from_device.restype = C.c_int
 lib.vpt_procedural_fill.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _vp]; lib.vpt_procedural_fill.restype = C.c_int
 lib.vpt_bricks_create.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_ulonglong)]; lib.vpt_bricks_create.restype = C.c_int
 lib.vpt_bricks_read.argtypes = [C.c_uint64, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_float)]; lib.vpt_bricks_read.restype = C.c_int
+lib.vpt_debug_sampler_compare.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_double)]
+lib.vpt_debug_sampler_compare.restype = C.c_int
 lib.vpt_bricks_destroy.argtypes = [C.c_uint64]; lib.vpt_bricks_destroy.restype = C.c_int
 lib.vpt_set_brick_volume.argtypes = [_vp, C.c_uint64, C.c_int, C.c_int, C.c_int]; lib.vpt_set_brick_volume.restype = C.c_int
 

@@ -115,7 +115,16 @@ k_generate(const FrameArgs fa)
 
     const SphereRec sph = load_sphere(fa.sphere);
     // one block = one 32x4 pixel tile, all passes of the chunk (amortises the octree / table staging above)
-    for (int pass = 0; pass < fa.n_passes; ++pass) {
+    // a small local frame (multi-GPU shard, low resolution) splits the chunk's passes over blockIdx.z: see launch_generate
+    const int pass_begin = blockIdx.z * fa.passes_per_block;
+    const int pass_end = min(fa.n_passes, pass_begin + fa.passes_per_block);
+    // blue-noise jitter of each pass, from the per-chunk table written by k_bn_prepare; the value of the NEXT pass is requested one
+    // iteration ahead (the load was the kernel's top stall: every pass started by waiting ~1 us for these 8 bytes)
+    const int bn_index = valid ? (y % 256) * 256 + (x % 256) : 0;
+    float2 bn_next = (valid && pass_begin < pass_end) ? __ldg(fa.bn_table + (size_t)pass_begin * 65536 + bn_index) : make_float2(0.f, 0.f);
+    for (int pass = pass_begin; pass < pass_end; ++pass) {
+    const float2 bnv = bn_next;
+    if (valid && pass + 1 < pass_end) bn_next = __ldg(fa.bn_table + (size_t)(pass + 1) * 65536 + bn_index);
     bool hit = false;
     float3 org = f3(0.f), dir = f3(0.f, 0.f, 1.f);
     uint32_t kdraws = 0;
@@ -129,9 +138,6 @@ k_generate(const FrameArgs fa)
         const uint32_t idx = (uint32_t)y * (uint32_t)g.width + (uint32_t)x;
         Rng rng; rng.init(idx, kp.iteration + (uint32_t)pass, 0u);
 
-        // blue-noise jitter of this pass, from the per-chunk table written by k_bn_prepare
-        const int bn_index = (y % 256) * 256 + (x % 256);
-        const float2 bnv = __ldg(fa.bn_table + (size_t)pass * 65536 + bn_index);
         const float bnx = bnv.x, bny = bnv.y;
         const float u = __fdividef(padd((float)x, bnx), (float)kp.resolution.x);
         const float v = __fdividef(padd((float)y, bny), (float)kp.resolution.y);
@@ -402,6 +408,13 @@ cudaError_t launch_generate(const FrameArgs& fa, int n_passes, cudaStream_t s)
 {
     dim3 grid((fa.geom.width + 31) / 32, (fa.geom.local_rows + 3) / 4, 1);
     FrameArgs a = fa; a.n_passes = n_passes;
+    // one block = one 32x4 pixel tile x a run of passes.  Keep >= ~8 waves of blocks (148 SMs x 7 resident blocks) so the tail of the
+    // grid does not idle the SMs when the local frame is small; never fewer than 4 passes per block (amortises the table staging).
+    int ppb = n_passes;
+    const long long tiles = (long long)grid.x * grid.y;
+    while (ppb > 4 && tiles * ((n_passes + ppb - 1) / ppb) < 8288) ppb = (ppb + 1) / 2;
+    a.passes_per_block = ppb;
+    grid.z = (unsigned)((n_passes + ppb - 1) / ppb);
     k_generate<<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
 }
@@ -444,6 +457,15 @@ cudaError_t trace_kernels_init(int max_ctas[4])
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brick_smem_bytes());
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas[3], k_trace_brick, kBrickThreads, brick_smem_bytes());
     return e;
+}
+
+cudaError_t launch_sampler_compare(unsigned long long tex, const float* pool, const int dims[3], int n, unsigned seed, double* d_out12, cudaStream_t s)
+{
+    BrickArgs ba;
+    ba.pool = pool; ba.dimx = dims[0]; ba.dimy = dims[1]; ba.dimz = dims[2];
+    ba.nbx = (dims[0] + 3) / 4; ba.nby = (dims[1] + 3) / 4; ba.nbz = (dims[2] + 3) / 4;
+    k_sampler_compare<<<592, 256, 0, s>>>((cudaTextureObject_t)tex, ba, n, seed, d_out12);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_trace_brick(const FrameArgs& fa, const float* pool, const int dims[3], int n_ctas, cudaStream_t s)

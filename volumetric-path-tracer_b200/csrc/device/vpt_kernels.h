@@ -37,6 +37,7 @@ struct FrameArgs {
     int       thin_lens;           // cam.lens_radius != 0
     const float2* bn_table;        // [pass][65536] blue-noise jitter of the chunk
     int       n_passes;            // passes in this chunk (k_generate loops over them)
+    int       passes_per_block;    // k_generate: passes handled by one block (blockIdx.z selects the run)
     int       debug_flags;         // development switches (0 in production)
     int       sched_min_lanes;     // trace scheduler: lanes an operation must gather before it pre-empts stepping
     unsigned* queue_count;
@@ -57,6 +58,7 @@ cudaError_t launch_trace(const FrameArgs& fa, const vpt_atmosphere* atm, bool le
 cudaError_t trace_kernels_init(int max_ctas[4]);      // [3]: k_trace_brick
 // fast mode: lean direct integrator reading the density from a brick pool (vpt_trace_brick.cuh); dims = voxels per axis
 cudaError_t launch_trace_brick(const FrameArgs& fa, const float* pool, const int dims[3], int n_ctas, cudaStream_t s);
+cudaError_t launch_sampler_compare(unsigned long long tex, const float* pool, const int dims[3], int n, unsigned seed, double* d_out12, cudaStream_t s);
 cudaError_t launch_fill_perlin(float* d_buffer, int dx, int dy, int dz, float scale, int seed, cudaStream_t s);
 cudaError_t launch_build_bricks(const float* d_dense, int dx, int dy, int dz, float* d_bricks, cudaStream_t s);
 // sky != null selects the environment_type == 0 variant (host copy of the caller's AtmosphereParameters)

@@ -56,39 +56,104 @@ VPT_DEV void brick_fetch(BrickSlot& bs, const float* src)
     bs.phase ^= 1u;
 }
 
-// weights of the texture unit's linear filter: 8 fractional bits
-VPT_DEV float q8(float f) { return floorf(f * 256.0f + 0.5f) * (1.0f / 256.0f); }
+// weights of the texture unit's linear filter: 9-bit fixed point with 8 fractional bits (CUDA programming guide, "Linear Filtering")
+// kWeightMode: 0 = rounded to the nearest 1/256, 1 = truncated to 1/256, 2 = full fp32 fraction (vpt_debug_sampler_compare measures
+// all three against tex3D on the device; the production value is kBrickWeightMode)
+#ifndef VPT_BRICK_WEIGHT_MODE
+#define VPT_BRICK_WEIGHT_MODE 0
+#endif
+constexpr int kBrickWeightMode = VPT_BRICK_WEIGHT_MODE;
+
+template <int kWeightMode>
+VPT_DEV float filter_weight(float f) {
+    if (kWeightMode == 0) return floorf(f * 256.0f + 0.5f) * (1.0f / 256.0f);
+    if (kWeightMode == 1) return floorf(f * 256.0f) * (1.0f / 256.0f);
+    return f;
+}
+
+struct BrickCell { int i, j, k; float a, b, c; };
+
+// texel cell and weights of a normalised, linearly filtered, clamp-addressed fetch at uvw: texel coordinate u * N - 0.5
+template <int kWeightMode>
+VPT_DEV BrickCell brick_cell(float3 uvw, const BrickArgs& ba)
+{
+    const float x = uvw.x * (float)ba.dimx - 0.5f, y = uvw.y * (float)ba.dimy - 0.5f, z = uvw.z * (float)ba.dimz - 0.5f;
+    const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    BrickCell q;
+    q.a = filter_weight<kWeightMode>(x - fx); q.b = filter_weight<kWeightMode>(y - fy); q.c = filter_weight<kWeightMode>(z - fz);
+    q.i = (int)fx; q.j = (int)fy; q.k = (int)fz;
+    // clamp addressing: a weight that rounded up to 1 moves to the next cell; below texel 0 both taps are texel 0; the upper edge
+    // needs nothing, the apron texels were clamped when the brick was built
+    if (q.a >= 1.0f) { q.a = 0.0f; ++q.i; }
+    if (q.b >= 1.0f) { q.b = 0.0f; ++q.j; }
+    if (q.c >= 1.0f) { q.c = 0.0f; ++q.k; }
+    if (q.i < 0) { q.i = 0; q.a = 0.0f; }
+    if (q.j < 0) { q.j = 0; q.b = 0.0f; }
+    if (q.k < 0) { q.k = 0; q.c = 0.0f; }
+    q.i = min(q.i, ba.dimx - 1); q.j = min(q.j, ba.dimy - 1); q.k = min(q.k, ba.dimz - 1);
+    return q;
+}
+
+VPT_DEV int brick_id(const BrickCell& q, const BrickArgs& ba) { return ((q.k >> 2) * ba.nby + (q.j >> 2)) * ba.nbx + (q.i >> 2); }
+
+// blend of the cell's eight texels inside a 5x5x5 brick at `brick`
+VPT_DEV float brick_blend(const float* brick, const BrickCell& q)
+{
+    const float* s = brick + ((q.k & 3) * 5 + (q.j & 3)) * 5 + (q.i & 3);
+    const float v000 = s[0], v100 = s[1], v010 = s[5], v110 = s[6], v001 = s[25], v101 = s[26], v011 = s[30], v111 = s[31];
+    const float a = q.a, b = q.b, c = q.c, na = 1.0f - a, nb = 1.0f - b, nc = 1.0f - c;
+    return na * nb * nc * v000 + a * nb * nc * v100 + na * b * nc * v010 + a * b * nc * v110
+         + na * nb * c * v001 + a * nb * c * v101 + na * b * c * v011 + a * b * c * v111;
+}
 
 VPT_DEV float brick_density(const VolumeRec& v, float3 p, const BrickArgs& ba, BrickSlot& bs, uint32_t& nfetch)
 {
     float3 uvw;
     if (!volume_coord(v, p, uvw)) return 0.0f;
-    // texel coordinates of a normalised, linearly filtered fetch: u * N - 0.5
-    float x = uvw.x * (float)ba.dimx - 0.5f, y = uvw.y * (float)ba.dimy - 0.5f, z = uvw.z * (float)ba.dimz - 0.5f;
-    float fx = floorf(x), fy = floorf(y), fz = floorf(z);
-    float a = q8(x - fx), b = q8(y - fy), c = q8(z - fz);
-    int i = (int)fx, j = (int)fy, k = (int)fz;
-    // clamp addressing: below texel 0 both taps are texel 0; a weight that rounded up to 1 moves to the next cell; the upper
-    // edge needs nothing, the apron texels were clamped when the brick was built
-    if (a >= 1.0f) { a = 0.0f; ++i; }
-    if (b >= 1.0f) { b = 0.0f; ++j; }
-    if (c >= 1.0f) { c = 0.0f; ++k; }
-    if (i < 0) { i = 0; a = 0.0f; }
-    if (j < 0) { j = 0; b = 0.0f; }
-    if (k < 0) { k = 0; c = 0.0f; }
-    i = min(i, ba.dimx - 1); j = min(j, ba.dimy - 1); k = min(k, ba.dimz - 1);
-    const int bx = i >> 2, by = j >> 2, bz = k >> 2;
-    const int id = (bz * ba.nby + by) * ba.nbx + bx;
+    const BrickCell q = brick_cell<kBrickWeightMode>(uvw, ba);
+    const int id = brick_id(q, ba);
     if (id != bs.resident) {
         brick_fetch(bs, ba.pool + (size_t)id * kBrickFloats);
         bs.resident = id;
         nfetch++;
     }
-    const float* s = bs.data + ((k & 3) * 5 + (j & 3)) * 5 + (i & 3);
-    const float v000 = s[0], v100 = s[1], v010 = s[5], v110 = s[6], v001 = s[25], v101 = s[26], v011 = s[30], v111 = s[31];
-    const float na = 1.0f - a, nb = 1.0f - b, nc = 1.0f - c;
-    return na * nb * nc * v000 + a * nb * nc * v100 + na * b * nc * v010 + a * b * nc * v110
-         + na * nb * c * v001 + a * nb * c * v101 + na * b * c * v011 + a * b * c * v111;
+    return brick_blend(bs.data, q);
+}
+
+// Diagnostic: software filter (three weight rules, bricks read straight from global memory) against the texture unit on `n`
+// pseudo-random points of the unit cube.  out[mode * 4 + {0,1,2,3}] = max |d|, sum |d|, number of bit-identical results, n.
+template <int kWeightMode>
+VPT_DEV float brick_sample_global(float3 uvw, const BrickArgs& ba)
+{
+    const BrickCell q = brick_cell<kWeightMode>(uvw, ba);
+    return brick_blend(ba.pool + (size_t)brick_id(q, ba) * kBrickFloats, q);
+}
+
+__global__ void k_sampler_compare(cudaTextureObject_t tex, const BrickArgs ba, int n, uint32_t seed, double* out)
+{
+    float mx[3] = { 0.f, 0.f, 0.f }; double sum[3] = { 0, 0, 0 }; unsigned long long same[3] = { 0, 0, 0 };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const PhiloxBlock r = philox4x32_10((uint32_t)i, 0u, seed);
+        const float3 uvw = f3(u32_to_unit(r.x), u32_to_unit(r.y), u32_to_unit(r.z));
+        const float t = tex3D<float>(tex, uvw.x, uvw.y, uvw.z);
+        const float s0 = brick_sample_global<0>(uvw, ba), s1 = brick_sample_global<1>(uvw, ba), s2 = brick_sample_global<2>(uvw, ba);
+        const float d[3] = { fabsf(s0 - t), fabsf(s1 - t), fabsf(s2 - t) };
+        const float sv[3] = { s0, s1, s2 };
+        for (int m = 0; m < 3; ++m) { mx[m] = fmaxf(mx[m], d[m]); sum[m] += d[m]; same[m] += (__float_as_uint(sv[m]) == __float_as_uint(t)) ? 1ull : 0ull; }
+    }
+    for (int m = 0; m < 3; ++m) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mx[m] = fmaxf(mx[m], __shfl_xor_sync(0xffffffffu, mx[m], o));
+            sum[m] += __shfl_xor_sync(0xffffffffu, sum[m], o);
+            same[m] += __shfl_xor_sync(0xffffffffu, same[m], o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            // max of non-negative doubles == max of their bit patterns
+            atomicMax(reinterpret_cast<unsigned long long*>(out + m * 4 + 0), (unsigned long long)__double_as_longlong((double)mx[m]));
+            atomicAdd(out + m * 4 + 1, sum[m]);
+            atomicAdd(out + m * 4 + 2, (double)same[m]);
+        }
+    }
 }
 
 // One tracking step, as walk_step<true> (vpt_trace.cuh) with the density fetched from the brick slot and the throughput kept in

@@ -466,6 +466,20 @@ int vpt_bricks_read(vpt_devptr_t d_pool, unsigned long long first_brick, unsigne
     return VPT_OK;
 }
 
+int vpt_debug_sampler_compare(vpt_tex_t tex, vpt_devptr_t d_pool, int dx, int dy, int dz, int n_points, unsigned seed, double out12[12]) {
+    if (!tex || !d_pool || !out12 || n_points < 1) return fail(nullptr, VPT_ERR_INVALID, "vpt_debug_sampler_compare: bad arguments");
+    double* d_out = nullptr;
+    VPT_CUDA(nullptr, cudaMalloc(&d_out, sizeof(double) * 12));
+    cudaError_t e = cudaMemset(d_out, 0, sizeof(double) * 12);
+    const int dims[3] = { dx, dy, dz };
+    if (e == cudaSuccess) e = vpt::launch_sampler_compare(tex, reinterpret_cast<const float*>((uintptr_t)d_pool), dims, n_points, seed, d_out, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out12, d_out, sizeof(double) * 12, cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(nullptr, VPT_ERR_CUDA, std::string("vpt_debug_sampler_compare: ") + cudaGetErrorString(e));
+    for (int m = 0; m < 3; ++m) out12[m * 4 + 3] = (double)n_points;
+    return VPT_OK;
+}
+
 int vpt_bricks_destroy(vpt_devptr_t d_pool) { if (d_pool) cudaFree((void*)(uintptr_t)d_pool); return VPT_OK; }
 
 int vpt_set_brick_volume(vpt_context* c, vpt_devptr_t d_pool, int dx, int dy, int dz) {

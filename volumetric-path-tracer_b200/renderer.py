@@ -181,6 +181,35 @@ class DistributedRenderer:
         self.r.close()
 
 
+class LevelAModule:
+    """Level (A) of the drop-in boundary driven the way the reference application drives its kernel (main.cpp:1221-1236, 1823-1829):
+    cuModuleLoad -> cuModuleGetFunction("volume_rt_kernel") -> cuLaunchKernel(grid (w/16+1, h/16+1), block (16,16), params[9]),
+    through the CUDA Driver API (cuda-python).  `Renderer` only supplies the parameter block."""
+
+    def __init__(self, cubin_path=None):
+        import os
+        from cuda.bindings import driver as drv
+        self.drv = drv
+        torch.cuda.current_stream()                                   # make sure the primary context exists and is current
+        path = cubin_path or os.path.join(os.path.dirname(N.LIB_PATH), "volume_rt_kernel_b200.cubin")
+        err, self.module = drv.cuModuleLoad(path.encode())
+        if int(err): raise N.VptError(f"cuModuleLoad({path}) -> {err}")
+        err, self.fn = drv.cuModuleGetFunction(self.module, b"volume_rt_kernel")
+        if int(err): raise N.VptError(f"cuModuleGetFunction(volume_rt_kernel) -> {err}")
+
+    def launch(self, r: "Renderer", sync=True):
+        """One progressive pass; the caller keeps doing ++iteration like the reference loop."""
+        gx, gy = int(r.width // 16) + 1, int(r.height // 16) + 1
+        err, = self.drv.cuLaunchKernel(self.fn, gx, gy, 1, 16, 16, 1, 0, 0, C.addressof(r.params.array), 0)
+        if int(err): raise N.VptError(f"cuLaunchKernel(volume_rt_kernel) -> {err}")
+        r.kp.iteration += 1
+        if sync: torch.cuda.synchronize()
+
+    def close(self):
+        if getattr(self, "module", None) is not None:
+            self.drv.cuModuleUnload(self.module); self.module = None
+
+
 def stripe_rows_of_rank(height, rank, n_ranks, stripe_rows):
     """Host-side mirror of the kernel's local-row -> global-row map (used by the CPU/gloo tests)."""
     if n_ranks == 1:
