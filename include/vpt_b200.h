@@ -231,6 +231,31 @@ int  vpt_bvh_destroy(vpt_devptr_t d_nodes, vpt_devptr_t d_leaves);
 /* AABB of one instance (GPU_VDB::Bounds, gpu_vdb.h:131-146): out6 = pmin, pmax. */
 void vpt_volume_bounds(const vpt_gpu_vdb* h_volume, float out6[6]);
 
+/* ---- Bruneton sky tables (replaces atmosphere::init, source/atmosphere/atmosphere.cpp:1177-1291 + atmosphere_kernels.cu) ------------
+ * Builds the Earth model of the reference (its spectra, density profiles, radii), reduces it to the AtmosphereParameters block the
+ * render path takes by value, precomputes the transmittance / irradiance / scattering / single-Mie tables on the device (own sm_100a
+ * kernels, four scattering orders) and wraps them as the four look-up textures with the reference's descriptors.  *out receives the
+ * complete block (scalars + texture objects; scratch buffer pointers null); free with vpt_atmosphere_destroy(handle).
+ * The tables reproduce the reference's build of the model, including the places where it departs from Bruneton's paper (later
+ * orders overwrite instead of accumulate because the host passes a float4 where its kernels read an int: quirk Q17; mie_extinction
+ * taken from the Mie scattering spectrum), except that table look-ups past the last texel are clamped where the reference reads
+ * beyond its buffers (atmosphere_kernels.cu:366-372): the outermost texels of orders >= 2 differ by construction. */
+typedef struct vpt_atmosphere_options {
+    int   use_constant_solar_spectrum;   /* main.cpp:1433 default 1 */
+    int   use_ozone;                     /* default 1 */
+    int   luminance_mode;                /* 0 NONE (default), 1 APPROXIMATE, 2 PRECOMPUTED (15 wavelengths) */
+    int   do_white_balance;              /* default 1 */
+    float exposure;                      /* default 1 */
+    int   num_scattering_orders;         /* default 4 */
+} vpt_atmosphere_options;
+void vpt_atmosphere_options_defaults(vpt_atmosphere_options* opt);
+int  vpt_atmosphere_precompute(const vpt_atmosphere_options* opt, vpt_atmosphere* out, void** handle_out);
+int  vpt_atmosphere_destroy(void* handle);
+/* Texel centres of a float4 texture (w x h, or w x h x d when d > 0) into host memory, 4 floats per texel, x fastest. */
+int  vpt_texture_read_f4(vpt_tex_t tex, int w, int h, int d, float* host_out);
+/* Diagnostic: tex3D<float> at n arbitrary normalised coordinates (uvw: 3 floats per point). */
+int  vpt_debug_texture_sample(vpt_tex_t tex, const float* uvw, int n, float* out);
+
 /* Thin-lens camera set-up (camera::update_camera, camera.h:110-129). */
 void vpt_camera_look_at(vpt_camera* cam, const float lookfrom[3], const float lookat[3], const float vup[3],
                         float vfov_deg, float aspect, float aperture);

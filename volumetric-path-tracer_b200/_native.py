@@ -154,7 +154,8 @@ EXPORTED_SYMBOLS = [
     "vpt_env_tables_create", "vpt_ins_load", "vpt_env_sky_tabulate",
     "vpt_octree_info", "vpt_octree_read_flat", "vpt_bvh_build", "vpt_bvh_read", "vpt_bvh_destroy", "vpt_env_tables_compute",
     "vpt_comm_get_unique_id", "vpt_comm_init", "vpt_comm_set_gather", "vpt_comm_wait", "vpt_comm_info", "vpt_comm_destroy",
-    "vpt_texture_create_3d_from_device", "vpt_procedural_fill", "vpt_bricks_create", "vpt_bricks_destroy", "vpt_set_brick_volume", "vpt_bricks_read", "vpt_debug_sampler_compare",
+    "vpt_texture_create_3d_from_device", "vpt_procedural_fill", "vpt_bricks_create", "vpt_bricks_destroy", "vpt_set_brick_volume", "vpt_bricks_read", "vpt_debug_sampler_compare", "vpt_atmosphere_options_defaults", "vpt_atmosphere_precompute", "vpt_atmosphere_destroy",
+    "vpt_texture_read_f4", "vpt_debug_texture_sample",
 ]
 
 # ---- prototypes ------------------------------------------------------------------------------------
@@ -204,6 +205,18 @@ lib.vpt_debug_sampler_compare.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_i
 lib.vpt_debug_sampler_compare.restype = C.c_int
 lib.vpt_bricks_destroy.argtypes = [C.c_uint64]; lib.vpt_bricks_destroy.restype = C.c_int
 lib.vpt_set_brick_volume.argtypes = [_vp, C.c_uint64, C.c_int, C.c_int, C.c_int]; lib.vpt_set_brick_volume.restype = C.c_int
+
+
+class atmosphere_options(C.Structure):
+    _fields_ = [("use_constant_solar_spectrum", C.c_int), ("use_ozone", C.c_int), ("luminance_mode", C.c_int), ("do_white_balance", C.c_int),
+                ("exposure", C.c_float), ("num_scattering_orders", C.c_int)]
+
+
+lib.vpt_atmosphere_options_defaults.argtypes = [C.POINTER(atmosphere_options)]; lib.vpt_atmosphere_options_defaults.restype = None
+lib.vpt_atmosphere_precompute.argtypes = [C.POINTER(atmosphere_options), C.POINTER(AtmosphereParameters), C.POINTER(_vp)]; lib.vpt_atmosphere_precompute.restype = C.c_int
+lib.vpt_atmosphere_destroy.argtypes = [_vp]; lib.vpt_atmosphere_destroy.restype = C.c_int
+lib.vpt_texture_read_f4.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]; lib.vpt_texture_read_f4.restype = C.c_int
+lib.vpt_debug_texture_sample.argtypes = [C.c_uint64, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float)]; lib.vpt_debug_texture_sample.restype = C.c_int
 
 
 class ins_header(C.Structure):

@@ -237,7 +237,7 @@ volume_rt_kernel(const vpt_camera cam, const vpt_light_list lights, const vpt_gp
             }
             continue;
         }
-        if (st.op == OP_STEP) walk_step<false>(st, fs, fa, tc, sph, nlook, &st.beta.x, 1);
+        if (st.op == OP_STEP) walk_step<false>(st, fs, fa, tc, sph, nlook);
     }
 
     // ---- environment term, guard, running mean, tonemap, buffer writes (:1838-1850, :2262-2316) ----------------------------------------

@@ -159,8 +159,7 @@ VPT_DEV void store_walk(const PoolView& pv, int s, const PathState& st)
 // kLean: single volume, no emission walk, no point lights -- the headline configuration; those features' code is compiled out
 // of that instantiation (smaller hot loop: the kernel is fetch-stall bound)
 template <bool kLean>
-VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph, uint32_t& nlook,
-                       float* beta, int beta_stride)      // the path's throughput: x, y, z at beta[0], beta[stride], beta[2 * stride]
+VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph, uint32_t& nlook)
 {
     const SceneTables& sc = fs.sc;
     const vpt_kernel_params& kp = fa.kp;
@@ -195,19 +194,31 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
     if (st.mode == W_DELTA) {
         if (st.alpha < 1.0f) st.alpha += density;
         if (pmul(tc.inv_max, density) > st.rng.next()) {
-            // colour terms are only consumed by an accepted collision: the reference evaluates them at every step and drops them
-            const float3 Cd = kLean ? fmax3(f3(0.0f), volume_color(fs.vol0, st.wpos)) : leaf_color(sc, fs.vol0, leaf, st.wpos);
-            const int index = int(floorf(fminf(fmaxf((density * tc.inv_max * 255.0f / kp.emission_pivot), 0.0f), 255.0f)));
-            const float3 density_color = reinterpret_cast<const float3*>(kp.density_color_texture)[index];
-            float3 b3 = f3(beta[0], beta[beta_stride], beta[2 * beta_stride]);     // in k_trace the throughput lives in the parked record
-            b3 *= (ld3(kp.albedo) * Cd * density_color / ld3(kp.extinction)) * float(kp.energy_inject);
-            beta[0] = b3.x; beta[beta_stride] = b3.y; beta[2 * beta_stride] = b3.z;
+            // Accepted collision.  The throughput update (colour grid + colour LUT look-ups) is NOT done here: one or two lanes of the
+            // stepping warp would sit on a dependent global load while thirty wait (22 % of the stall samples on the 1024^3 grid).
+            // The density and the leaf are handed to scatter_event(), which the service round runs for many rays at once.
+            st.trv = density;                                       // free during a delta walk (the ratio walk re-initialises it)
+            if (!kLean) st.aux.x = __int_as_float(leaf);            // aux is free during a delta walk, too
             st.op = OP_GLUE; st.exit_reason = EX_SCATTER;
         }
     } else {
         st.trv = pmul(st.trv, pfma(-tc.sigma_r_inv, psub(density, tc.sigma_c), 1.0f));   // 1 - (rho - sigma_c) * sigma_r_inv, fused as in the reference SASS
         if (length(f3(st.trv)) < VPT_EPS) { st.op = OP_GLUE; st.exit_reason = EX_TR_DONE; }
     }
+}
+
+// The throughput factor of an accepted collision: albedo * Cd * density_colour / extinction * energy_inject (reference `sample`,
+// render_kernel.cu:1664-1675).  Cd is the leaf's colour at the collision point -- the leaf located at the step's START, as the reference
+// does -- and the colour LUT is indexed by density / sigma_max; the reference evaluates both at every step and drops them unless accepted.
+template <bool kLean>
+VPT_DEV void scatter_event(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc)
+{
+    const vpt_kernel_params& kp = fa.kp;
+    const float density = st.trv;
+    const float3 Cd = kLean ? fmax3(f3(0.0f), volume_color(fs.vol0, st.wpos)) : leaf_color(fs.sc, fs.vol0, __float_as_int(st.aux.x), st.wpos);
+    const int index = int(floorf(fminf(fmaxf((density * tc.inv_max * 255.0f / kp.emission_pivot), 0.0f), 255.0f)));
+    const float3 density_color = reinterpret_cast<const float3*>(kp.density_color_texture)[index];
+    st.beta *= (ld3(kp.albedo) * Cd * density_color / ld3(kp.extinction)) * float(kp.energy_inject);
 }
 
 // ---- OP_TRBEGIN: reference Tr prologue (:1150-1167); the walk starts from (st.wpos, st.wdir) -----------------
@@ -274,7 +285,7 @@ VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, 
         case PH_AFTER_DELTA: {
             st.pos = st.wpos;                                       // `sample` advances the caller's ray_pos
             int obj = 1;
-            if (st.exit_reason == EX_SCATTER) st.mi = true;
+            if (st.exit_reason == EX_SCATTER) { scatter_event<kLean>(st, fs, fa, tc); st.mi = true; }
             if (st.exit_reason == EX_DISTANCE) obj = 2;             // compiled reference: obj = 2 on every distance exit (Q4)
             if (st.first_walk) {
                 st.depth = st.mi ? length(st.org - st.pos) : .0f;
@@ -537,7 +548,7 @@ k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atm
                     break;
                 }
                 if (cur >= 0) {
-                    walk_step<kLean>(st, fs, fa, tc, sph, nlook, &pv.f(9, cur), kPool); lane_steps++;
+                    walk_step<kLean>(st, fs, fa, tc, sph, nlook); lane_steps++;
                     if (st.op != OP_STEP) {                        // walk ended: park the ray with its new tag
                         store_walk(pv, cur, st);
                         if (cur == 0) tag0 = st.op; else if (cur == 1) tag1 = st.op; else tag2 = st.op;

@@ -56,32 +56,45 @@ VPT_DEV void brick_fetch(BrickSlot& bs, const float* src)
     bs.phase ^= 1u;
 }
 
-// weights of the texture unit's linear filter: 9-bit fixed point with 8 fractional bits (CUDA programming guide, "Linear Filtering")
-// kWeightMode: 0 = rounded to the nearest 1/256, 1 = truncated to 1/256, 2 = full fp32 fraction (vpt_debug_sampler_compare measures
-// all three against tex3D on the device; the production value is kBrickWeightMode)
+// The texture unit's linear filter, measured on the device (tools/tex_filter_probe.py, profiles/r02d_tex_filter_probe.txt): the texel
+// coordinate x = u * N - 0.5 is formed EXACTLY (no intermediate rounding of u * N) and the fraction is then rounded to the nearest
+// 1/256 (9-bit fixed point, 8 fractional bits, as the CUDA programming guide states).  An fp32 evaluation of u * N - 0.5 lands on the
+// other side of a rounding boundary for ~0.5 % of the coordinates when N is not a power of two; the product of a 24-bit and an 11-bit
+// number is exact in double, so the coordinate is formed there.
+// kWeightMode: 0 = this rule (production), 1 = fraction truncated to 1/256, 2 = full-precision fraction, 3 = rule 0 with the coordinate in
+// fp32 (vpt_debug_sampler_compare reports modes 0..2 against tex3D).
 #ifndef VPT_BRICK_WEIGHT_MODE
 #define VPT_BRICK_WEIGHT_MODE 0
 #endif
 constexpr int kBrickWeightMode = VPT_BRICK_WEIGHT_MODE;
 
-template <int kWeightMode>
-VPT_DEV float filter_weight(float f) {
-    if (kWeightMode == 0) return floorf(f * 256.0f + 0.5f) * (1.0f / 256.0f);
-    if (kWeightMode == 1) return floorf(f * 256.0f) * (1.0f / 256.0f);
-    return f;
-}
-
 struct BrickCell { int i, j, k; float a, b, c; };
 
 // texel cell and weights of a normalised, linearly filtered, clamp-addressed fetch at uvw: texel coordinate u * N - 0.5
 template <int kWeightMode>
+VPT_DEV void filter_axis(float u, int n, int& cell, float& w)
+{
+    if (kWeightMode == 3) {
+        const float x = u * (float)n - 0.5f, fl = floorf(x);
+        cell = (int)fl; w = floorf((x - fl) * 256.0f + 0.5f) * (1.0f / 256.0f);
+        return;
+    }
+    const double x = (double)u * (double)n - 0.5, fl = floor(x);
+    const float f = (float)(x - fl);
+    cell = (int)fl;
+    if (kWeightMode == 0) w = (float)(floor((x - fl) * 256.0 + 0.5) * (1.0 / 256.0));
+    else if (kWeightMode == 1) w = floorf(f * 256.0f) * (1.0f / 256.0f);
+    else w = f;
+}
+
+// texel cell and weights of a normalised, linearly filtered, clamp-addressed fetch at uvw
+template <int kWeightMode>
 VPT_DEV BrickCell brick_cell(float3 uvw, const BrickArgs& ba)
 {
-    const float x = uvw.x * (float)ba.dimx - 0.5f, y = uvw.y * (float)ba.dimy - 0.5f, z = uvw.z * (float)ba.dimz - 0.5f;
-    const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
     BrickCell q;
-    q.a = filter_weight<kWeightMode>(x - fx); q.b = filter_weight<kWeightMode>(y - fy); q.c = filter_weight<kWeightMode>(z - fz);
-    q.i = (int)fx; q.j = (int)fy; q.k = (int)fz;
+    filter_axis<kWeightMode>(uvw.x, ba.dimx, q.i, q.a);
+    filter_axis<kWeightMode>(uvw.y, ba.dimy, q.j, q.b);
+    filter_axis<kWeightMode>(uvw.z, ba.dimz, q.k, q.c);
     // clamp addressing: a weight that rounded up to 1 moves to the next cell; below texel 0 both taps are texel 0; the upper edge
     // needs nothing, the apron texels were clamped when the brick was built
     if (q.a >= 1.0f) { q.a = 0.0f; ++q.i; }
@@ -187,9 +200,7 @@ VPT_DEV void walk_step_brick(PathState& st, const FrameShared& fs, const FrameAr
     if (st.mode == W_DELTA) {
         if (st.alpha < 1.0f) st.alpha += density;
         if (pmul(tc.inv_max, density) > st.rng.next()) {
-            const int index = int(floorf(fminf(fmaxf((density * tc.inv_max * 255.0f / kp.emission_pivot), 0.0f), 255.0f)));
-            const float3 density_color = reinterpret_cast<const float3*>(kp.density_color_texture)[index];
-            st.beta *= (ld3(kp.albedo) * f3(1.0f) * density_color / ld3(kp.extinction)) * float(kp.energy_inject);
+            st.trv = density;                                       // throughput update: scatter_event() in the bookkeeping round
             st.op = OP_GLUE; st.exit_reason = EX_SCATTER;
         }
     } else {

@@ -459,6 +459,40 @@ class Scene:
             if t: t.destroy()
 
 
+class Atmosphere:
+    """The Bruneton sky model + its four precomputed look-up textures, built by the library (vpt_atmosphere_precompute:
+    replaces atmosphere::init, source/atmosphere/atmosphere.cpp:1177-1291).  `apply(scene.atmos)` fills a Scene's
+    AtmosphereParameters block in place."""
+
+    SHAPES = dict(transmittance=(256, 64, 0), scattering=(256, 128, 32), irradiance=(256, 64, 0), single_mie=(256, 128, 32))
+
+    def __init__(self, use_constant_solar_spectrum=True, use_ozone=True, luminance=0, white_balance=True, exposure=1.0, orders=4):
+        o = N.atmosphere_options()
+        lib.vpt_atmosphere_options_defaults(C.byref(o))
+        o.use_constant_solar_spectrum = int(use_constant_solar_spectrum); o.use_ozone = int(use_ozone); o.luminance_mode = int(luminance)
+        o.do_white_balance = int(white_balance); o.exposure = float(exposure); o.num_scattering_orders = int(orders)
+        self.params = N.AtmosphereParameters(); self.handle = C.c_void_p(0)
+        check(lib.vpt_atmosphere_precompute(C.byref(o), C.byref(self.params), C.byref(self.handle)), None, "vpt_atmosphere_precompute")
+
+    def apply(self, atmos):
+        C.memmove(C.byref(atmos), C.byref(self.params), C.sizeof(N.AtmosphereParameters))
+
+    def destroy(self):
+        if self.handle: lib.vpt_atmosphere_destroy(self.handle); self.handle = C.c_void_p(0)
+
+
+def read_atmosphere_tables(atmos):
+    """The four look-up textures of an AtmosphereParameters block (this library's or the reference's) as numpy arrays [..., 4]."""
+    out = {}
+    for name, tex in (("transmittance", atmos.transmittance_texture), ("scattering", atmos.scattering_texture),
+                      ("irradiance", atmos.irradiance_texture), ("single_mie", atmos.single_mie_scattering_texture)):
+        w, h, d = Atmosphere.SHAPES[name]
+        a = np.empty((max(d, 1), h, w, 4), dtype=np.float32)
+        check(lib.vpt_texture_read_f4(tex, w, h, d, a.ctypes.data_as(C.POINTER(C.c_float))), None, "vpt_texture_read_f4")
+        out[name] = a if d else a[0]
+    return out
+
+
 def read_bvh(d_nodes, d_leaves, n):
     """Host view of a BVH in the reference layout (either builder's): child / parent fields as indices (-1 = none)."""
     hn = (N.BVHNode * max(n - 1, 1))(); hl = (N.BVHNode * n)()
