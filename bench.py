@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) check of the timed frame against the reference kernel")
     ap.add_argument("--generic-kernel", action="store_true", help="A/B: force the generic trace kernel instantiation")
+    ap.add_argument("--ref-jit61", action="store_true", help="with --impl reference: load the reference kernel as compute_61 PTX (its shipped form) and let the driver JIT it")
     ap.add_argument("--level-a", action="store_true", help="time the level (A) module: volume_rt_kernel_b200.cubin loaded and launched through the "
                     "Driver API exactly like the reference kernel (one launch + synchronize per spp), instead of the wavefront library")
     ap.add_argument("--fast", action="store_true", help="config 4: trace from the brick pool (TMA-staged software sampler) instead of the 3-D texture")
@@ -246,19 +247,25 @@ def main():
             scene = V.Scene(scene.instances[:n_inst], device=dev, env="Barce_Rooftop_C_3k.hdr")
             config["reference_instances"] = n_inst
         orc = oracle_ref.RefOracle(); orc.load_kernels()
+        which = orc.UNMODIFIED
+        kernel_note = "source/render_kernel.cu compiled unmodified with -O3 --use_fast_math --maxrregcount=128 for sm_100a"
+        if args.ref_jit61:
+            # the reference as shipped: PTX for compute_61 (source/CMakeLists.txt:133), JIT-compiled by the driver at module load (untimed)
+            orc.load_candidate(os.path.join(oracle_ref.REF_DIR, "render_kernel_ref_cc61.ptx")); which = orc.CANDIDATE
+            kernel_note = "source/render_kernel.cu as compute_61 PTX (the reference's own build), JIT-compiled by the driver for this GPU"
         r = V.Renderer(scene, WIDTH, HEIGHT, kp=kp)
         r.params.p_oct.value = orc.build_octree(scene.h_volumes, n_inst)      # the reference's own octree builder
         def step():
             r.kp.iteration = 0
             for _ in range(SPP):                               # main.cpp:1823-1829: launch, ++iteration, cudaDeviceSynchronize
-                orc.launch(r.params.array, WIDTH, HEIGHT, orc.UNMODIFIED, sync=True)
+                orc.launch(r.params.array, WIDTH, HEIGHT, which, sync=True)
                 r.kp.iteration += 1
         sampler.start()
         ms, wall = timed_steps(step, args.steps, args.warmup, None, flush_buf, sampler)
         clocks = sampler.stop()
         val = samples_per_step * args.steps / (ms * 1e-3) / 1e6
         config.update({"launch_protocol": "reference main loop: 1 launch + cudaDeviceSynchronize per spp, grid (W/16+1,H/16+1)x(16,16)",
-                       "kernel": "source/render_kernel.cu compiled unmodified with -O3 --use_fast_math --maxrregcount=128 for sm_100a",
+                       "kernel": kernel_note,
                        "octree": "reference build_octree (bvh_kernels.cu:582-604)"})
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -275,6 +282,8 @@ def main():
     if args.chunk: opts["passes_per_chunk"] = args.chunk
     if args.sched_min_lanes: opts["sched_min_lanes"] = args.sched_min_lanes
     if args.generic_kernel: opts["generic_kernel"] = 1
+    for kv in filter(None, os.environ.get("VPT_BENCH_OPTIONS", "").split(",")):     # A/B runs: e.g. VPT_BENCH_OPTIONS=trace_slots=3
+        k, v = kv.split("="); opts[k.strip()] = int(v)
     stream = torch.cuda.current_stream().cuda_stream
     if world > 1:
         dr = V.DistributedRenderer(scene, WIDTH, HEIGHT, kp=kp, stripe_rows=8, options=opts)

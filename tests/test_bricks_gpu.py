@@ -48,7 +48,9 @@ def test_procedural_fill_against_reference_fill_kernel():
     print(f"reference fill: {int((b == -7.0).sum())} of {b.size} voxels untouched, finite {bool(np.isfinite(b).all())}, range [{np.nanmin(b):.3g}, {np.nanmax(b):.3g}]")
     assert np.isfinite(a).all() and a.min() < -0.3 and a.max() > 0.3, "Perlin noise spans negative and positive densities (quirk Q10)"
     print(f"fill: max |ours - reference| = {np.abs(a - b).max():.3g} (jitter bound ~ {0.1 / min(dims) * 2:.3g}), corr {np.corrcoef(a, b)[0, 1]:.6f}")
-    assert np.abs(a - b).max() < 2e-3
+    # the reference jitters every sample position with an UNINITIALISED curand state (quirk Q14; its -O3 build does not even run): the
+    # -G build used here draws some jitter, ours draws none -- the fields agree to the jitter's reach (~2 * scale / dim) and correlate to 1e-5
+    assert np.abs(a - b).max() < 1e-2 and np.corrcoef(a, b)[0, 1] > 0.9999
     info = vol.rec.vdb_info
     assert (info.max_density, info.min_density, info.voxelsize) == (1.0, 0.0, 1.0) and (info.dim.x, info.dim.y, info.dim.z) == dims
     assert info.bmax.x - info.bmin.x == dims[0]
@@ -73,17 +75,18 @@ def test_brick_pool_layout(perlin):
 
 
 def test_software_filter_against_texture_unit(perlin):
-    """The brick sampler's blend against tex3D on a million random points, for the three candidate weight rules (rounded / truncated
-    to 1/256, full fp32).  The production rule must stay within the texture unit's own quantisation step."""
+    """The brick sampler's blend against tex3D on a million random points: the production rule (the texture unit's hierarchical 8-bit
+    corner weights, fitted on the device: tools/tex_weight_fit.py) must be bit-identical on nearly every fetch and within an ulp on the
+    rest; the two naive per-axis rules are reported for contrast."""
     out = (C.c_double * 12)()
     tex = perlin.rec.vdb_info.density_texture
     V._native.check(V.lib.vpt_debug_sampler_compare(tex, perlin.brick_pool, *perlin.dims, 1 << 20, 7, out), None, "vpt_debug_sampler_compare")
-    names = ("weights rounded to 1/256", "weights truncated to 1/256", "full fp32 weights")
+    names = ("texture-unit rule (integer corner weights, z -> x -> y)", "per-axis weights truncated to 1/256", "per-axis full fp32 weights")
     for m in range(3):
         mx, sm, same, n = out[4 * m:4 * m + 4]
         print(f"software filter vs tex3D, {names[m]}: max |d| {mx:.3g}, mean |d| {sm / n:.3g}, bit-identical {100 * same / n:.2f} %")
     prod = 0
-    assert out[4 * prod] < 5e-3 and out[4 * prod + 1] / out[4 * prod + 3] < 5e-4
+    assert out[4 * prod] < 1e-6 and out[4 * prod + 2] / out[4 * prod + 3] > 0.99
 
 
 @needs_ref
@@ -102,8 +105,8 @@ def test_parity_mode_on_the_procedural_volume_against_reference(perlin):
 
 
 def test_fast_mode_statistics_against_parity_mode(perlin):
-    """Same seeds, same control flow: a pixel differs only where a software-filtered density landed on the other side of an
-    accept / reject comparison.  Report the flipped fraction of ONE pass and bound it."""
+    """Same seeds, same control flow, and a software filter that reproduces the texture unit bit for bit on 99.8 % of the fetches (one
+    ulp off on the rest): the brick / TMA path has to meet the SAME per-pixel tolerance as the texture path."""
     scene = scene_of(perlin)
     kw = dict(ray_depth=2)
     par = V.Renderer(scene, 640, 400, kp=make_kp(**kw)); fast = V.Renderer(scene, 640, 400, kp=make_kp(**kw), cam=par.cam, options={"count_stats": 1})
@@ -116,10 +119,10 @@ def test_fast_mode_statistics_against_parity_mode(perlin):
     print(f"fast vs parity, 1 pass: flipped {frac:.4g}; {cnt['lookups']} look-ups, {cnt['brick_fetches']} bricks staged by TMA "
           f"({cnt['lookups'] / max(1, cnt['brick_fetches']):.2f} look-ups per staged brick), {cnt['rays']} rays")
     assert cnt["brick_fetches"] > 0 and cnt["lookups"] >= cnt["brick_fetches"]
-    assert np.isfinite(b).all() and frac <= 0.02
+    assert np.isfinite(b).all() and frac <= MAX_FLIPPED
     assert abs(float(b.mean()) - float(a.mean())) <= 0.01 * float(a.mean())
     # depth buffer: first-hit distance only moves where the first walk's decisions moved
-    assert flipped_fraction(fast.buffers.depth.cpu().numpy()[:, None], par.buffers.depth.cpu().numpy()[:, None]) <= 0.02
+    assert flipped_fraction(fast.buffers.depth.cpu().numpy()[:, None], par.buffers.depth.cpu().numpy()[:, None]) <= MAX_FLIPPED
 
 
 @needs_ref

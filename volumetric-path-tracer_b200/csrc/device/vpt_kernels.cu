@@ -419,41 +419,44 @@ cudaError_t launch_generate(const FrameArgs& fa, int n_passes, cudaStream_t s)
     return cudaGetLastError();
 }
 
-static size_t trace_smem_bytes() { return (size_t)kTraceWarps * kRayWords * kPool * sizeof(float); }
+static size_t trace_smem_bytes(int slots) { return (size_t)kTraceWarps * kRayWords * 32 * slots * sizeof(float); }
 
 // atm != null selects the volumetric path integrator variant (Kernel_params.integrator != 0); lean selects the instantiation
-// without multi-volume lists, emission walk and point lights (the caller guarantees none of them is in play)
-template <int kInteg, bool kLean>
+// without multi-volume lists, emission walk and point lights (the caller guarantees none of them is in play); slots = rays per lane
+template <int kInteg, bool kLean, int kSlots>
 static cudaError_t launch_trace_t(const FrameArgs& fa, const vpt_atmosphere* atm, int n_ctas, cudaStream_t s)
 {
-    if constexpr (kInteg != 0) k_trace<kInteg, kLean><<<n_ctas, kTraceThreads, trace_smem_bytes(), s>>>(fa, *atm);
-    else                       k_trace<kInteg, kLean><<<n_ctas, kTraceThreads, trace_smem_bytes(), s>>>(fa, NoAtmo{});
+    if constexpr (kInteg != 0) k_trace<kInteg, kLean, kSlots><<<n_ctas, kTraceThreads, trace_smem_bytes(kSlots), s>>>(fa, *atm);
+    else                       k_trace<kInteg, kLean, kSlots><<<n_ctas, kTraceThreads, trace_smem_bytes(kSlots), s>>>(fa, NoAtmo{});
     return cudaGetLastError();
 }
 
-cudaError_t launch_trace(const FrameArgs& fa, const vpt_atmosphere* atm, bool lean, int n_ctas, cudaStream_t s)
+cudaError_t launch_trace(const FrameArgs& fa, const vpt_atmosphere* atm, bool lean, int slots, int n_ctas, cudaStream_t s)
 {
-    if (atm) return launch_trace_t<1, false>(fa, atm, n_ctas, s);
-    return lean ? launch_trace_t<0, true>(fa, nullptr, n_ctas, s) : launch_trace_t<0, false>(fa, nullptr, n_ctas, s);
+    if (atm) return launch_trace_t<1, false, 3>(fa, atm, n_ctas, s);
+    if (slots == 2) return lean ? launch_trace_t<0, true, 2>(fa, nullptr, n_ctas, s) : launch_trace_t<0, false, 2>(fa, nullptr, n_ctas, s);
+    return lean ? launch_trace_t<0, true, 3>(fa, nullptr, n_ctas, s) : launch_trace_t<0, false, 3>(fa, nullptr, n_ctas, s);
 }
 
-// Once per context (= per device): opt the three instantiations into their dynamic shared memory and record how many CTAs
-// of each fit on an SM.  The attribute is a per-device property of the function, so this must not be a process-wide static.
-template <int kInteg, bool kLean>
+// Once per context (= per device): opt the instantiations into their dynamic shared memory and record how many CTAs of each fit
+// on an SM.  The attribute is a per-device property of the function, so this must not be a process-wide static.
+template <int kInteg, bool kLean, int kSlots>
 static cudaError_t trace_init_t(int* max_ctas)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_trace<kInteg, kLean>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes());
+    cudaError_t e = cudaFuncSetAttribute(k_trace<kInteg, kLean, kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes(kSlots));
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_ctas, k_trace<kInteg, kLean>, kTraceThreads, trace_smem_bytes());
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_ctas, k_trace<kInteg, kLean, kSlots>, kTraceThreads, trace_smem_bytes(kSlots));
 }
 
 static size_t brick_smem_bytes() { return (size_t)kBrickThreads * kBrickBytes; }
 
-cudaError_t trace_kernels_init(int max_ctas[4])
+cudaError_t trace_kernels_init(int max_ctas[6])
 {
-    cudaError_t e = trace_init_t<0, false>(&max_ctas[0]);
-    if (e == cudaSuccess) e = trace_init_t<0, true>(&max_ctas[1]);
-    if (e == cudaSuccess) e = trace_init_t<1, false>(&max_ctas[2]);
+    cudaError_t e = trace_init_t<0, false, 3>(&max_ctas[0]);
+    if (e == cudaSuccess) e = trace_init_t<0, true, 3>(&max_ctas[1]);
+    if (e == cudaSuccess) e = trace_init_t<1, false, 3>(&max_ctas[2]);
+    if (e == cudaSuccess) e = trace_init_t<0, false, 2>(&max_ctas[4]);
+    if (e == cudaSuccess) e = trace_init_t<0, true, 2>(&max_ctas[5]);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brick_smem_bytes());
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas[3], k_trace_brick, kBrickThreads, brick_smem_bytes());
     return e;

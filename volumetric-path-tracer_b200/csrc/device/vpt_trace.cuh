@@ -38,11 +38,9 @@ enum Phase : int {
 enum ExitReason : int { EX_NONE = 0, EX_OUTSIDE, EX_DISTANCE, EX_SCATTER, EX_TR_DONE };
 enum TrKind : int { TR_SUN = 0, TR_POINT = 1, TR_SPHERE = 2 };
 
-#ifndef VPT_TRACE_SLOTS
-#define VPT_TRACE_SLOTS 3
-#endif
-constexpr int kSlots = VPT_TRACE_SLOTS;   // rays per lane (2 or 3)
-constexpr int kPool = 32 * kSlots;        // rays per warp
+// rays per lane: 3 (4 CTAs per SM, <= 128 registers) or 2 (5 CTAs per SM, <= 96 registers: more warps in flight, the better
+// trade when every look-up misses all caches -- 1024^3 grid: trace 157 -> 99 ms; slower when the look-ups hit L2)
+constexpr int trace_min_ctas(int slots) { return slots == 2 ? 5 : kTraceMinCtas; }
 constexpr int kRayWords = 34;             // 32-bit words per ray in shared memory
 constexpr int kTraceWarps = kTraceThreads / 32;
 
@@ -74,13 +72,15 @@ struct TraceConsts {
 
 // ---- ray record <-> registers ------------------------------------------------------------------------------
 // pool layout: word w of slot j of lane l at pool[w * kPool + j * 32 + l]  (bank == lane: conflict-free)
+template <int kPool>                                             // rays per warp = 32 * rays per lane
 struct PoolView {
     float* w;                                                    // this warp's kRayWords * kPool words, already offset by the lane
     VPT_DEV float& f(int word, int slot) const { return w[word * kPool + slot * 32]; }
     VPT_DEV uint32_t& u(int word, int slot) const { return reinterpret_cast<uint32_t*>(w)[word * kPool + slot * 32]; }
 };
 
-VPT_DEV void store_ray(const PoolView& pv, int s, const PathState& st)
+template <class PV>
+VPT_DEV void store_ray(const PV& pv, int s, const PathState& st)
 {
     pv.f(0, s) = st.pos.x;  pv.f(1, s) = st.pos.y;  pv.f(2, s) = st.pos.z;
     pv.f(3, s) = st.dir.x;  pv.f(4, s) = st.dir.y;  pv.f(5, s) = st.dir.z;
@@ -111,7 +111,8 @@ VPT_DEV void ray_rng_init(PathState& st, const FrameArgs& fa, uint32_t k)
     st.rng.init(idx, fa.kp.iteration + st.pass, k);
 }
 
-VPT_DEV void load_ray(const PoolView& pv, int s, PathState& st, const FrameArgs& fa)
+template <class PV>
+VPT_DEV void load_ray(const PV& pv, int s, PathState& st, const FrameArgs& fa)
 {
     st.pos = f3(pv.f(0, s), pv.f(1, s), pv.f(2, s));    st.dir = f3(pv.f(3, s), pv.f(4, s), pv.f(5, s));
     st.L = f3(pv.f(6, s), pv.f(7, s), pv.f(8, s));      st.beta = f3(pv.f(9, s), pv.f(10, s), pv.f(11, s));
@@ -134,7 +135,8 @@ VPT_DEV void load_ray(const PoolView& pv, int s, PathState& st, const FrameArgs&
 // in word 30: the packed word is carried as is and patched on the way out (unpacking/packing everything cost 5 % of the kernel's
 // instructions).  beta is not carried either: the one event that changes it (a scatter) updates it in place in shared memory.
 constexpr uint32_t kExitMask = 7u << 6;
-VPT_DEV void load_walk(const PoolView& pv, int s, PathState& st, const FrameArgs& fa)
+template <class PV>
+VPT_DEV void load_walk(const PV& pv, int s, PathState& st, const FrameArgs& fa)
 {
     st.wpos = f3(pv.f(12, s), pv.f(13, s), pv.f(14, s)); st.wdir = f3(pv.f(15, s), pv.f(16, s), pv.f(17, s));
     st.aux = f3(pv.f(18, s), pv.f(19, s), pv.f(20, s));
@@ -146,7 +148,8 @@ VPT_DEV void load_walk(const PoolView& pv, int s, PathState& st, const FrameArgs
     ray_rng_init(st, fa, k);
 }
 
-VPT_DEV void store_walk(const PoolView& pv, int s, const PathState& st)
+template <class PV>
+VPT_DEV void store_walk(const PV& pv, int s, const PathState& st)
 {
     pv.f(12, s) = st.wpos.x; pv.f(13, s) = st.wpos.y; pv.f(14, s) = st.wpos.z;
     pv.f(18, s) = st.aux.x; pv.f(19, s) = st.aux.y; pv.f(20, s) = st.aux.z;
@@ -159,7 +162,8 @@ VPT_DEV void store_walk(const PoolView& pv, int s, const PathState& st)
 // kLean: single volume, no emission walk, no point lights -- the headline configuration; those features' code is compiled out
 // of that instantiation (smaller hot loop: the kernel is fetch-stall bound)
 template <bool kLean>
-VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph, uint32_t& nlook)
+VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph, uint32_t& nlook,
+                       float* beta = nullptr, int beta_stride = 0)   // kLean: the path's throughput in the parked record (x, y, z one stride apart)
 {
     const SceneTables& sc = fs.sc;
     const vpt_kernel_params& kp = fa.kp;
@@ -194,11 +198,21 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
     if (st.mode == W_DELTA) {
         if (st.alpha < 1.0f) st.alpha += density;
         if (pmul(tc.inv_max, density) > st.rng.next()) {
-            // Accepted collision.  The throughput update (colour grid + colour LUT look-ups) is NOT done here: one or two lanes of the
-            // stepping warp would sit on a dependent global load while thirty wait (22 % of the stall samples on the 1024^3 grid).
-            // The density and the leaf are handed to scatter_event(), which the service round runs for many rays at once.
-            st.trv = density;                                       // free during a delta walk (the ratio walk re-initialises it)
-            if (!kLean) st.aux.x = __int_as_float(leaf);            // aux is free during a delta walk, too
+            if (kLean) {
+                // single volume: the colour terms are two cached loads; updating the parked throughput here measured faster than a
+                // deferred update (trace 7.1 ms against 7.8 ms on the headline frame)
+                const float3 Cd = fmax3(f3(0.0f), volume_color(fs.vol0, st.wpos));
+                const int index = int(floorf(fminf(fmaxf((density * tc.inv_max * 255.0f / kp.emission_pivot), 0.0f), 255.0f)));
+                const float3 density_color = reinterpret_cast<const float3*>(kp.density_color_texture)[index];
+                float3 b3 = f3(beta[0], beta[beta_stride], beta[2 * beta_stride]);
+                b3 *= (ld3(kp.albedo) * Cd * density_color / ld3(kp.extinction)) * float(kp.energy_inject);
+                beta[0] = b3.x; beta[beta_stride] = b3.y; beta[2 * beta_stride] = b3.z;
+            } else {
+                // instanced / emissive scenes: the per-leaf colour look-ups are deferred to scatter_event() in the service round, where
+                // many rays run them at once instead of one or two lanes of a stepping warp (fireball: trace 212 -> 185 ms)
+                st.trv = density;                                   // free during a delta walk (the ratio walk re-initialises it)
+                st.aux.x = __int_as_float(leaf);                    // aux is free during a delta walk, too
+            }
             st.op = OP_GLUE; st.exit_reason = EX_SCATTER;
         }
     } else {
@@ -210,12 +224,11 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
 // The throughput factor of an accepted collision: albedo * Cd * density_colour / extinction * energy_inject (reference `sample`,
 // render_kernel.cu:1664-1675).  Cd is the leaf's colour at the collision point -- the leaf located at the step's START, as the reference
 // does -- and the colour LUT is indexed by density / sigma_max; the reference evaluates both at every step and drops them unless accepted.
-template <bool kLean>
 VPT_DEV void scatter_event(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc)
 {
     const vpt_kernel_params& kp = fa.kp;
     const float density = st.trv;
-    const float3 Cd = kLean ? fmax3(f3(0.0f), volume_color(fs.vol0, st.wpos)) : leaf_color(fs.sc, fs.vol0, __float_as_int(st.aux.x), st.wpos);
+    const float3 Cd = leaf_color(fs.sc, fs.vol0, __float_as_int(st.aux.x), st.wpos);
     const int index = int(floorf(fminf(fmaxf((density * tc.inv_max * 255.0f / kp.emission_pivot), 0.0f), 255.0f)));
     const float3 density_color = reinterpret_cast<const float3*>(kp.density_color_texture)[index];
     st.beta *= (ld3(kp.albedo) * Cd * density_color / ld3(kp.extinction)) * float(kp.energy_inject);
@@ -285,7 +298,7 @@ VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, 
         case PH_AFTER_DELTA: {
             st.pos = st.wpos;                                       // `sample` advances the caller's ray_pos
             int obj = 1;
-            if (st.exit_reason == EX_SCATTER) { scatter_event<kLean>(st, fs, fa, tc); st.mi = true; }
+            if (st.exit_reason == EX_SCATTER) { if (!kLean) scatter_event(st, fs, fa, tc); st.mi = true; }
             if (st.exit_reason == EX_DISTANCE) obj = 2;             // compiled reference: obj = 2 on every distance exit (Q4)
             if (st.first_walk) {
                 st.depth = st.mi ? length(st.org - st.pos) : .0f;
@@ -427,8 +440,8 @@ VPT_DEV void write_sample(const PathState& st, const FrameArgs& fa)
 // caller's AtmosphereParameters in the kernel (sky radiance decides whether a transmittance walk is run at all)
 struct NoAtmo { int pad[4]; };
 
-template <int kInteg, bool kLean>
-__global__ void __launch_bounds__(kTraceThreads, kTraceMinCtas)
+template <int kInteg, bool kLean, int kSlots>
+__global__ void __launch_bounds__(kTraceThreads, trace_min_ctas(kSlots))
 k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atmosphere, NoAtmo>::type atm)
 {
     __shared__ FrameShared fs;
@@ -447,7 +460,8 @@ k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atm
     tc.sun_dir = sun_direction(kp.azimuth, kp.elevation);
     const SphereRec sph = load_sphere(fa.sphere);
 
-    PoolView pv; pv.w = pool_smem + (size_t)warp * kRayWords * kPool + lane;
+    constexpr int kPool = 32 * kSlots;
+    PoolView<kPool> pv; pv.w = pool_smem + (size_t)warp * kRayWords * kPool + lane;
     constexpr int OP_NOSLOT = 15;                                 // third slot disabled when kSlots == 2
     int tag0 = OP_IDLE, tag1 = OP_IDLE, tag2 = (kSlots > 2) ? OP_IDLE : OP_NOSLOT;   // operation each of my rays waits for
 
@@ -548,7 +562,7 @@ k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atm
                     break;
                 }
                 if (cur >= 0) {
-                    walk_step<kLean>(st, fs, fa, tc, sph, nlook); lane_steps++;
+                    walk_step<kLean>(st, fs, fa, tc, sph, nlook, &pv.f(9, cur), kPool); lane_steps++;
                     if (st.op != OP_STEP) {                        // walk ended: park the ray with its new tag
                         store_walk(pv, cur, st);
                         if (cur == 0) tag0 = st.op; else if (cur == 1) tag1 = st.op; else tag2 = st.op;

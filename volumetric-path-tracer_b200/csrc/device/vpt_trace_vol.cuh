@@ -144,7 +144,7 @@ VPT_DEV void advance_vol(PathState& st, const FrameShared& fs, const FrameArgs& 
             return;
         case VP_AFTER_DELTA:
             st.pos = st.wpos;
-            if (st.exit_reason == EX_SCATTER) { scatter_event<false>(st, fs, fa, tc); st.mi = true; }
+            if (st.exit_reason == EX_SCATTER) { scatter_event(st, fs, fa, tc); st.mi = true; }
             if (st.first_walk) {                                    // this walk is also the depth pass's (same start, same draws)
                 st.depth = st.mi ? length(st.org - st.pos) : .0f;
                 if (st.alpha < 1.0f) st.alpha += st.alpha;

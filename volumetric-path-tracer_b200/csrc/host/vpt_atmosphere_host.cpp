@@ -121,7 +121,9 @@ void fill_model(vpt_atmosphere& P, const Spectra& s, const double lambdas[3], co
     P.absorption_density.layers[1] = layer(0.0, 0.0, 0.0, -1.0 / 15000.0, 8.0 / 3.0);
     P.absorption_extinction = f3d(interp(s.wl, s.absorption, lambdas[0]), interp(s.wl, s.absorption, lambdas[1]), interp(s.wl, s.absorption, lambdas[2]));
     P.ground_albedo = f3d(interp(s.wl, s.albedo, lambdas[0]), interp(s.wl, s.albedo, lambdas[1]), interp(s.wl, s.albedo, lambdas[2]));
-    P.mu_s_min = (float)cos(120.0 / 180.0 * M_PI);
+    // pi is a FLOAT literal in the reference's translation unit (common/helper_math.h:47 redefines M_PI), widened to double for
+    // the product: cos gives -0.50000006, not -0.5 (atmosphere.cpp:746-747)
+    P.mu_s_min = (float)cos(120.0 / 180.0 * (double)3.14159265358979323846f);
     P.use_luminance = o.luminance_mode == 1 ? 1 : o.luminance_mode == 2 ? 2 : 0;
     double wp[3] = { 1.0, 1.0, 1.0 };
     if (o.do_white_balance) white_point(s, wp);

@@ -96,6 +96,7 @@ int vpt_create(vpt_context** out) {
     VPT_CREATE(cudaGetDeviceProperties(&prop, c->device));
     if (prop.major < 10) { std::string m = "vpt_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ", kernels are built for sm_100a only"; free_context(c); return fail(nullptr, VPT_ERR_UNSUPPORTED, m); }
     c->num_sms = prop.multiProcessorCount;
+    c->l2_bytes = (size_t)prop.l2CacheSize;
     VPT_CREATE(cudaMalloc(&c->d_scene, sizeof(vpt::SceneTables)));
     VPT_CREATE(cudaMalloc(&c->d_counters, sizeof(unsigned) * 4));
     VPT_CREATE(cudaMalloc(&c->d_stats, sizeof(unsigned long long) * 8));
@@ -116,6 +117,7 @@ int vpt_set_option(vpt_context* c, const char* key, int value) {
     if (k == "passes_per_chunk") { if (value < 0 || value > 64) return fail(c, VPT_ERR_INVALID, "passes_per_chunk must be 0 (automatic) or 1..64"); c->chunk_auto = value == 0; if (value) c->passes_per_chunk = value; }
     else if (k == "max_scratch_mb") { if (value < 64) return fail(c, VPT_ERR_INVALID, "max_scratch_mb must be >= 64"); c->max_scratch_bytes = (size_t)value << 20; }
     else if (k == "gather_async") { c->gather_async = value ? 1 : 0; }
+    else if (k == "trace_slots") { if (value != 0 && value != 2 && value != 3) return fail(c, VPT_ERR_INVALID, "trace_slots must be 0 (by grid size), 2 or 3"); c->trace_slots = value; }
     else if (k == "ctas_per_sm") { if (value < 0 || value > 8) return fail(c, VPT_ERR_INVALID, "ctas_per_sm must be 0..8"); c->ctas_per_sm = value; }
     else if (k == "sched_min_lanes") { if (value < 1 || value > 32) return fail(c, VPT_ERR_INVALID, "sched_min_lanes must be 1..32"); c->sched_min_lanes = value; }
     else if (k == "debug_flags") { c->debug_flags = value; }
@@ -309,7 +311,19 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
     fa.queue_count = c->d_counters; fa.queue_head = c->d_counters + 1;
     fa.planeA = c->d_planeA; fa.planeB = c->d_planeB; fa.planeC = c->d_planeC; fa.planeD = planeD ? c->d_planeD : nullptr;
 
-    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : c->max_ctas[c->brick_pool ? 3 : vol_integ ? 2 : (lean ? 1 : 0)];
+    // rays per lane: 3 by default; 2 (one more CTA per SM) when a look-up is a chain of cache misses -- a density grid that cannot live
+    // in L2 (every look-up a DRAM round trip) or long per-leaf instance lists (dependent loads): warps in flight then matter more than
+    // rays per warp.  Measured: 1024^3 grid 158 -> 104 ms, 512^3 92 -> 77 ms, 1000 instances 94 -> 82 ms; the
+    // L2-resident scenes lose with it (dragon 7.1 -> 8.2 ms, fireball 185 -> 282 ms).
+    int slots = 3;
+    if (!vol_integ && !c->brick_pool) {
+        if (c->trace_slots) slots = c->trace_slots;
+        else {
+            vpt::SceneEntry ent;
+            if (vpt::scene_registry_find(d_root, &ent) && (ent.max_grid_bytes > 2ull * c->l2_bytes || ent.n >= 64)) slots = 2;
+        }
+    }
+    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : c->max_ctas[c->brick_pool ? 3 : vol_integ ? 2 : (slots == 2 ? (lean ? 5 : 4) : (lean ? 1 : 0))];
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int trace_ctas = c->num_sms * ctas_per_sm;
 
@@ -335,7 +349,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         VPT_CUDA(c, timed(3, [&] { return vpt::launch_bn_prepare((void*)kp.blue_noise_buffer, c->d_bn_table, (int)np, bn_limit, stream); }));   // jitter table + advance
         VPT_CUDA(c, timed(0, [&] { return vpt::launch_generate(fa, (int)np, stream); }));
         if (c->brick_pool) VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace_brick(fa, c->brick_pool, c->brick_dims, trace_ctas, stream); }));
-        else VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, vol_integ ? &atmo : nullptr, lean, trace_ctas, stream); }));
+        else VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, vol_integ ? &atmo : nullptr, lean, slots, trace_ctas, stream); }));
         const bool last = (done + np == n_passes);
         if (c->gather_pending) { int rc = vpt::comm_before_accum_write(c, stream); if (rc != VPT_OK) return rc; }
         VPT_CUDA(c, timed(2, [&] { return vpt::launch_resolve(fa, sky, (int)np, 1, last ? 1 : 0, stream); }));

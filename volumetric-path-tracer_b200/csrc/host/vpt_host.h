@@ -24,7 +24,9 @@ struct vpt_context {
     bool   scene_single_volume = false;
     size_t cap_vrec = 0;              // VolumeRec capacity (grows with the instance count)
     int*   h_pinned = nullptr;        // one pinned word for the 4-byte read-back a foreign octree needs
-    int    max_ctas[4] = {0, 0, 0, 0};   // trace kernel occupancy: [0] generic, [1] lean, [2] volumetric path, [3] brick (fast mode)
+    int    max_ctas[6] = {0, 0, 0, 0, 0, 0};   // trace kernel occupancy: [0] generic, [1] lean, [2] volumetric path, [3] brick (fast mode), [4] generic / [5] lean at 2 rays per lane
+    int    trace_slots = 0;              // option "trace_slots": rays per lane of k_trace, 0 = by grid size (2 when the grid is larger than twice the L2)
+    size_t l2_bytes = 0;
     const float* brick_pool = nullptr; int brick_dims[3] = {0, 0, 0};   // fast mode: density of volume 0 as a brick pool (vpt_set_brick_volume)
     int    force_generic = 0;        // option "generic_kernel": 1 = never use the lean trace instantiation (A/B and tests)
     vpt::SceneTables* d_scene = nullptr;
@@ -89,6 +91,7 @@ struct SceneEntry {
     size_t       total_indices = 0;
     int          max_leaf_count = 0;
     unsigned     any_flags = 0;              // bit0: some instance has a colour grid, bit1: some instance has an emission grid
+    unsigned long long max_grid_bytes = 0;   // density grid of the largest instance (float voxels): picks the trace kernel's rays per lane
 };
 bool scene_registry_find(vpt_devptr_t d_root, SceneEntry* out);
 

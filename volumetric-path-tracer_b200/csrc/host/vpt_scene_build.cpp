@@ -67,7 +67,11 @@ int vpt_octree_build(const vpt_gpu_vdb* h_volumes, int n, vpt_devptr_t* d_root_o
     root->max_extinction = .0f; root->min_extinction = 3.402823466e+38F; root->voxel_size = 3.402823466e+38F;
     root->depth = 4;
     unsigned any_flags = 0;
+    unsigned long long max_grid_bytes = 0;
     for (int i = 0; i < n; ++i) {
+        const vpt_i3 dm = h_volumes[i].vdb_info.dim;
+        const unsigned long long gb = (dm.x > 0 && dm.y > 0 && dm.z > 0) ? 4ull * (unsigned long long)dm.x * (unsigned long long)dm.y * (unsigned long long)dm.z : 0ull;
+        if (gb > max_grid_bytes) max_grid_bytes = gb;
         float b[6]; vpt::instance_bounds_host(h_volumes[i], b);
         root->bbox.pmax.x = fmaxf(root->bbox.pmax.x, b[3]); root->bbox.pmax.y = fmaxf(root->bbox.pmax.y, b[4]); root->bbox.pmax.z = fmaxf(root->bbox.pmax.z, b[5]);
         root->bbox.pmin.x = fminf(root->bbox.pmin.x, b[0]); root->bbox.pmin.y = fminf(root->bbox.pmin.y, b[1]); root->bbox.pmin.z = fminf(root->bbox.pmin.z, b[2]);
@@ -87,7 +91,7 @@ int vpt_octree_build(const vpt_gpu_vdb* h_volumes, int n, vpt_devptr_t* d_root_o
     vpt::SceneEntry ent; ent.device = device; ent.n = n;
     ent.root6[0] = root->bbox.pmin.x; ent.root6[1] = root->bbox.pmin.y; ent.root6[2] = root->bbox.pmin.z;
     ent.root6[3] = root->bbox.pmax.x; ent.root6[4] = root->bbox.pmax.y; ent.root6[5] = root->bbox.pmax.z;
-    ent.max_extinction = root->max_extinction; ent.min_extinction = root->min_extinction; ent.any_flags = any_flags;
+    ent.max_extinction = root->max_extinction; ent.min_extinction = root->min_extinction; ent.any_flags = any_flags; ent.max_grid_bytes = max_grid_bytes;
     std::vector<int> counts(585);
     std::vector<vpt::OctInternal> internal(vpt::kOctInternalNodes);
     std::vector<uint2> leaf_list(vpt::kOctLeaves);
