@@ -286,7 +286,7 @@ def main():
         k, v = kv.split("="); opts[k.strip()] = int(v)
     stream = torch.cuda.current_stream().cuda_stream
     if world > 1:
-        dr = V.DistributedRenderer(scene, WIDTH, HEIGHT, kp=kp, stripe_rows=8, options=opts)
+        dr = V.DistributedRenderer(scene, WIDTH, HEIGHT, kp=kp, stripe_rows=8, options=opts, exchange=os.environ.get("VPT_EXCHANGE", "p2p"))
         r = dr.r
         def step():
             r.kp.iteration = 0
@@ -382,13 +382,13 @@ def main():
     if rank == 0 and args.level_a:
         roofline = {"bound": "hbm", "kernel": "volume_rt_kernel (level A megakernel)", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
                     "note": "the level (A) entry is the strict drop-in, not the measured hot path: no per-kernel breakdown is taken for it"}
-    if rank == 0 and not args.level_a:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
-        def render_only():                                  # rank-local work only: no collective here, the other ranks have moved on
+    kt = cnt = None
+    per_rank_ms = None
+    if not args.level_a:
+        # rank-local work only, on EVERY rank (per-rank kernel times show the stripe imbalance); the library's all-gather is switched
+        # off for these runs -- a collective that only some ranks enter would hang the job
+        if dr is not None: dr.set_gather(False)
+        def render_only():
             r.kp.iteration = 0
             r.render(SPP, stream=stream)
         r.set_option("profile", 1); r.kernel_times()         # per-kernel CUDA events, production kernels
@@ -400,6 +400,18 @@ def main():
         torch.cuda.synchronize()
         cnt = r.counters()
         r.set_option("count_stats", 0)
+        if dr is not None: dr.set_gather(True)
+        if world > 1:
+            mine = {k: round(v["ms"] / 2, 4) for k, v in kt.items()}
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+            per_rank_ms = gathered
+    if rank == 0 and not args.level_a:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
         n_steps_prof = 2
         samples = r.n_local * SPP * n_steps_prof
         launches = max(1, kt["trace"]["launches"])
@@ -426,14 +438,14 @@ def main():
                     "density_lookups_per_sample": lookups_per_sample, "rays_traced_per_sample": cnt["rays"] / max(1, samples),
                     "bricks_staged_per_lookup": (cnt["brick_fetches"] / max(1, cnt["lookups"])) if args.fast else None,
                     "step_loop_simt_efficiency": simt, "service_round_lanes": cnt["lane_services"] / max(1, cnt["warp_service_rounds"]),
-                    "kernel_ms_per_step": {k: v["ms"] / n_steps_prof for k, v in kt.items()},
+                    "kernel_ms_per_step": {k: v["ms"] / n_steps_prof for k, v in kt.items()}, "kernel_ms_per_step_by_rank": per_rank_ms,
                     "step": {"bytes_per_sample": bytes_per_sample, "achieved": step_gbs, "achieved_per_gpu": step_gbs / world, "frac": step_gbs / world / peak,
                              "note": "whole step charged with SURVEY 8(d)'s 88 B + 32 B x lookups per sample; per-GPU rate over one GPU's peak"},
                     "note": "dragon.vdb is 425 KB: volume lookups are served by L1/TEX/L2, DRAM only sees the ray queue and the sample planes; "
                             "the path is bound by latency / instruction issue, not HBM (SURVEY 8(d)); see profiles/"}
 
     cpu_base = None
-    if rank == 0 and not args.no_cpu_baseline and args.config in (1, 2):
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config in (1, 2):      # N = 1 only
         cpu_base = cpu_baseline_sample(V, scene, r.cam, kp, WIDTH, HEIGHT)
 
     if rank == 0:

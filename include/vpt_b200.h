@@ -79,6 +79,24 @@ int  vpt_comm_wait(vpt_context* ctx, void* stream);
 int  vpt_comm_info(vpt_context* ctx, int* nccl_version, int* rank, int* n_ranks);
 int  vpt_comm_destroy(vpt_context* ctx);
 
+/* Peer-memory exchange: the same result without NCCL and without a separate gather step, for up to 8 GPUs of one NVLink / NVSwitch
+ * domain (one process per GPU).  Every rank allocates ONE exchange block {flags, full-frame float3 accumulators, optional display words}
+ * and exports it as a CUDA IPC handle (vpt_comm_p2p_export: also applies vpt_set_partition); the application hands all handles to all
+ * ranks (64 bytes each, rank order) and every rank maps its peers (vpt_comm_p2p_import).  From then on the LAST resolve kernel of every
+ * vpt_render_pass(es) call stores each finished pixel straight into every rank's frame at its global position (all-gather and stripe
+ * un-permutation fused into the producing kernel, over peer mappings), bracketed by two flag exchanges in peer memory: "my previous frame
+ * has been consumed" at the start of the call, "my stripes are in place" at the end; the call's stream work ends with a wait for all
+ * peers, so after it the frame returned by vpt_comm_p2p_frame is complete on every rank, bit-identical to a single-GPU frame.
+ * vpt_comm_p2p_enable(ctx, 0) suspends the exchange for rank-local work (calls that not every rank makes); vpt_comm_p2p_status reports
+ * how many flag waits gave up (a wait abandons after 10 s instead of hanging the GPU: a rank died or made fewer calls). */
+#define VPT_P2P_HANDLE_BYTES 64
+int  vpt_comm_p2p_export(vpt_context* ctx, int rank, int n_ranks, int stripe_rows, unsigned width, unsigned height, int with_display,
+                         unsigned char handle_out[VPT_P2P_HANDLE_BYTES]);
+int  vpt_comm_p2p_import(vpt_context* ctx, const unsigned char* handles /* n_ranks x VPT_P2P_HANDLE_BYTES, rank order */);
+int  vpt_comm_p2p_frame(vpt_context* ctx, vpt_devptr_t* d_full_accum_f3, vpt_devptr_t* d_full_display_u32);
+int  vpt_comm_p2p_enable(vpt_context* ctx, int on);
+int  vpt_comm_p2p_status(vpt_context* ctx, unsigned long long* abandoned_waits);
+
 /* ---- the hot path --------------------------------------------------------------------------------
  * vpt_render_pass   replaces ONE launch of the reference `volume_rt_kernel` (render_kernel.cu:2216):
  *                   same inputs, same buffer updates (accum/depth/cost running means, display, raw,

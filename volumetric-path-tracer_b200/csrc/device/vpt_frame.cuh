@@ -90,8 +90,23 @@ VPT_DEV float3 ld3(const vpt_f3& v) { return f3(v.x, v.y, v.z); }
 
 // global row of a local row under the interleaved-stripe partition (identity for one rank)
 VPT_DEV int global_row(const FrameGeom& g, int lr) {
-    const int s = lr / g.stripe_h;
+    const int s = g.stripe_shift >= 0 ? (lr >> g.stripe_shift) : lr / g.stripe_h;
     return (s * g.n_ranks + g.rank) * g.stripe_h + (lr - s * g.stripe_h);
+}
+
+// The pixel word a ray carries (queue record, parked record).  One rank: the pixel index itself.  Several ranks: (local row << 16) | x --
+// the Philox stream is keyed by the GLOBAL pixel every time a ray is un-parked and the sample is written at the LOCAL pixel, and from
+// this form both are a shift / multiply-add away (a runtime division on the un-park path cost 5 % of the trace kernel).
+VPT_DEV uint32_t ray_pixel_word(const FrameGeom& g, int lr, int x) {
+    return g.n_ranks > 1 ? ((uint32_t)lr << 16) | (uint32_t)x : (uint32_t)lr * (uint32_t)g.width + (uint32_t)x;
+}
+VPT_DEV uint32_t ray_global_pixel(const FrameGeom& g, uint32_t w) {
+    if (g.n_ranks <= 1) return w;
+    return (uint32_t)global_row(g, (int)(w >> 16)) * (uint32_t)g.width + (w & 0xffffu);
+}
+VPT_DEV uint32_t ray_local_pixel(const FrameGeom& g, uint32_t w) {
+    if (g.n_ranks <= 1) return w;
+    return (w >> 16) * (uint32_t)g.width + (w & 0xffffu);
 }
 
 // radical inverse of int(xi*100) in `BASE` (reference vanDerCorput, gpu_vdb/camera.h:49-62)

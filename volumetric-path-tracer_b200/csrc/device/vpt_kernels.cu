@@ -226,7 +226,7 @@ k_generate(const FrameArgs fa)
             // 24-byte record (+16 B origin when the lens is not a pinhole): direction + entry distance, ids + RNG position
             const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
             fa.queue_dir[slot] = make_float4(dir.x, dir.y, dir.z, t_min);
-            fa.queue_id[slot] = make_uint2(lp, (uint32_t)pass | (kdraws << 6) | ((uint32_t)obj << 16) | ((uint32_t)prestepped << 18));
+            fa.queue_id[slot] = make_uint2(ray_pixel_word(g, lr, x), (uint32_t)pass | (kdraws << 6) | ((uint32_t)obj << 16) | ((uint32_t)prestepped << 18));
             if (prestepped) fa.queue_aux[slot] = make_float4(wstart.x, wstart.y, wstart.z, 0.f);      // where stepping starts
             else if (fa.thin_lens) fa.queue_aux[slot] = make_float4(org.x, org.y, org.z, 0.f);   // thin lens: per-ray origin
         }
@@ -242,11 +242,12 @@ k_generate(const FrameArgs fa)
 // kSky 2: volumetric path integrator, which always ends on the sky (:1752); kSky 0: HDRI environment -- that variant
 // takes a 16-byte dummy so it keeps its small parameter block and register budget.
 struct NoSky { int pad[4]; };
+struct PeerFlagPtrs { unsigned long long* p[kMaxPeers]; };
 
 template <int kSky>
 __global__ void __launch_bounds__(256)
 k_resolve(const FrameArgs fa, const typename std::conditional<kSky != 0, vpt_atmosphere, NoSky>::type atmo,
-          const int n_passes, const int sampled, const int write_display)
+          const int n_passes, const int sampled, const int write_display, const PeerFrames peers)
 {
     const FrameGeom& g = fa.geom;
     const vpt_kernel_params& kp = fa.kp;
@@ -266,18 +267,17 @@ k_resolve(const FrameArgs fa, const typename std::conditional<kSky != 0, vpt_atm
     if (have_prev || !sampled) { accum = accum_buf[lp]; costv = cost_buf[lp]; depthv = depth_buf[lp]; }
     float tr = .0f;
 
-    for (int p = 0; p < n_passes; ++p) {
+    // one pass of the running mean; A (and B, C for a hit sample) are the pass's plane records, loaded by the caller
+    auto one_pass = [&](const int p, const float4 A, const float4 B, const float4 C) {
         const uint32_t iteration = kp.iteration + (uint32_t)p;
         float3 value = f3(1.0f);                                // WHITE when nothing is sampled (:2248)
         float depth = .0f;
         tr = .0f;
         if (sampled) {
             const size_t s = (size_t)p * g.n_local + lp;
-            const float4 A = fa.planeA[s];
             const float3 ray_dir = f3(A.x, A.y, A.z);
             float3 beta = f3(1.0f), L = f3(0.0f);
             if (__float_as_uint(A.w) != kMissSentinel) {          // hit sample: the trace kernel wrote all three planes
-                const float4 B = fa.planeB[s], C = fa.planeC[s];
                 beta = f3(C.x, C.y, C.z); L = f3(B.x, B.y, B.z);
                 depth = B.w; tr = A.w;
             }
@@ -315,6 +315,18 @@ k_resolve(const FrameArgs fa, const typename std::conditional<kSky != 0, vpt_atm
             costv = costv + (f3(0.f) - costv) / (float)(iteration + 1);
             depthv = depthv + (depth - depthv) / (float)(iteration + 1);
         }
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        for (int p = 0; p < n_passes; ++p) {
+            float4 A = zero4, B = zero4, C = zero4;
+            if (sampled) {
+                const size_t s = (size_t)p * g.n_local + lp;
+                A = fa.planeA[s];
+                if (__float_as_uint(A.w) != kMissSentinel) { B = fa.planeB[s]; C = fa.planeC[s]; }
+            }
+            one_pass(p, A, B, C);
+        }
     }
     accum_buf[lp] = accum; cost_buf[lp] = costv; depth_buf[lp] = depthv;
 
@@ -327,8 +339,44 @@ k_resolve(const FrameArgs fa, const typename std::conditional<kSky != 0, vpt_atm
         const unsigned int r = (unsigned int)(255.0f * fminf(powf(fmaxf(val.x, 0.0f), (float)(1.0 / 2.2)), 1.0f));
         const unsigned int gg = (unsigned int)(255.0f * fminf(powf(fmaxf(val.y, 0.0f), (float)(1.0 / 2.2)), 1.0f));
         const unsigned int b = (unsigned int)(255.0f * fminf(powf(fmaxf(val.z, 0.0f), (float)(1.0 / 2.2)), 1.0f));
-        reinterpret_cast<unsigned int*>(kp.display_buffer)[lp] = 0xff000000 | (r << 16) | (gg << 8) | b;
+        const unsigned int word = 0xff000000 | (r << 16) | (gg << 8) | b;
+        reinterpret_cast<unsigned int*>(kp.display_buffer)[lp] = word;
         reinterpret_cast<float4*>(kp.raw_buffer)[lp] = make_float4(val.x, val.y, val.z, tr);
+        if (peers.n > 0 && peers.display[0]) {
+            const size_t gp = (size_t)y * g.width + (lp - (uint32_t)lr * (uint32_t)g.width);
+            #pragma unroll
+            for (int p = 0; p < kMaxPeers; ++p) if (p < peers.n) peers.display[p][gp] = word;
+        }
+    }
+    // multi-GPU exchange fused into the producer: this pixel's running mean goes to its global position in every rank's full frame
+    if (peers.n > 0 && peers.accum[0]) {
+        const size_t gp = (size_t)y * g.width + (lp - (uint32_t)lr * (uint32_t)g.width);
+        #pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p) if (p < peers.n) { float* a = peers.accum[p] + 3 * gp; a[0] = accum.x; a[1] = accum.y; a[2] = accum.z; }
+    }
+}
+
+__global__ void k_peer_signal(PeerFlagPtrs fl, int n, int rank, int which, unsigned long long epoch)
+{
+    const int p = threadIdx.x;
+    if (p >= n) return;
+    __threadfence_system();                                    // everything this stream stored before (peer frames included) ...
+    unsigned long long* slot = fl.p[p] + which * kPeerFlagStride + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(slot), "l"(epoch) : "memory");   // ... is visible before the flag
+}
+
+__global__ void k_peer_wait(unsigned long long* local, int n, int which, unsigned long long epoch)
+{
+    const int p = threadIdx.x;
+    if (p >= n) return;
+    const unsigned long long* slot = local + which * kPeerFlagStride + p;
+    unsigned long long t0 = 0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
+        if (v >= epoch) break;
+        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) { atomicAdd(local + 2 * kPeerFlagStride, 1ull); break; }     // 10 s: a rank is gone -- report, do not hang the GPU
+        __nanosleep(200);
     }
 }
 
@@ -480,13 +528,29 @@ cudaError_t launch_trace_brick(const FrameArgs& fa, const float* pool, const int
     return cudaGetLastError();
 }
 
-cudaError_t launch_resolve(const FrameArgs& fa, const vpt_atmosphere* sky, int n_passes, int sampled, int write_display, cudaStream_t s)
+cudaError_t launch_resolve(const FrameArgs& fa, const vpt_atmosphere* sky, int n_passes, int sampled, int write_display, const PeerFrames* peers, cudaStream_t s)
 {
     const int threads = 256;
     const int blocks = (fa.geom.n_local + threads - 1) / threads;
-    if (sky && fa.kp.integrator != 0) k_resolve<2><<<blocks, threads, 0, s>>>(fa, *sky, n_passes, sampled, write_display);
-    else if (sky)                     k_resolve<1><<<blocks, threads, 0, s>>>(fa, *sky, n_passes, sampled, write_display);
-    else                              k_resolve<0><<<blocks, threads, 0, s>>>(fa, NoSky{}, n_passes, sampled, write_display);
+    const PeerFrames pf = peers ? *peers : PeerFrames{};
+    // (tried for frames of less than two waves of blocks -- multi-GPU shards: fetching the records of four passes at once before the
+    // order-dependent running mean; slower there too, 0.28 vs 0.21 ms on a 1/8 shard of the 1080p frame)
+    if (sky && fa.kp.integrator != 0) k_resolve<2><<<blocks, threads, 0, s>>>(fa, *sky, n_passes, sampled, write_display, pf);
+    else if (sky)                     k_resolve<1><<<blocks, threads, 0, s>>>(fa, *sky, n_passes, sampled, write_display, pf);
+    else                              k_resolve<0><<<blocks, threads, 0, s>>>(fa, NoSky{}, n_passes, sampled, write_display, pf);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_signal(unsigned long long* const peer_flags[kMaxPeers], int n, int rank, int which, unsigned long long epoch, cudaStream_t s)
+{
+    PeerFlagPtrs fl; for (int p = 0; p < kMaxPeers; ++p) fl.p[p] = p < n ? peer_flags[p] : nullptr;
+    k_peer_signal<<<1, 32, 0, s>>>(fl, n, rank, which, epoch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_wait(unsigned long long* local_flags, int n, int which, unsigned long long epoch, cudaStream_t s)
+{
+    k_peer_wait<<<1, 32, 0, s>>>(local_flags, n, which, epoch);
     return cudaGetLastError();
 }
 

@@ -20,6 +20,7 @@ struct FrameGeom {
     int local_rows;         // rows stored locally (padded so every rank holds the same count)
     int n_local;            // local_rows * width
     int stripe_h, n_ranks, rank;
+    int stripe_shift;       // log2(stripe_h) when it is a power of two (index arithmetic without a division), else -1
 };
 
 // Everything a per-frame kernel needs, passed by value (about 600 B of kernel parameter space).
@@ -62,7 +63,17 @@ cudaError_t launch_sampler_compare(unsigned long long tex, const float* pool, co
 cudaError_t launch_fill_perlin(float* d_buffer, int dx, int dy, int dz, float scale, int seed, cudaStream_t s);
 cudaError_t launch_build_bricks(const float* d_dense, int dx, int dy, int dz, float* d_bricks, cudaStream_t s);
 // sky != null selects the environment_type == 0 variant (host copy of the caller's AtmosphereParameters)
-cudaError_t launch_resolve(const FrameArgs& fa, const vpt_atmosphere* sky, int n_passes, int sampled, int write_display, cudaStream_t s);
+// Peer-memory exchange (multi-GPU, csrc/host/vpt_comm.cpp): the call's LAST resolve kernel stores every finished pixel straight into the
+// full-frame buffer of every rank (its own included) at the pixel's global position, over NVLink peer mappings -- the all-gather and
+// the stripe un-permutation fused into the kernel that produces the values.
+constexpr int kMaxPeers = 8;
+struct PeerFrames { int n = 0; float* accum[kMaxPeers] = {}; unsigned int* display[kMaxPeers] = {}; };
+cudaError_t launch_resolve(const FrameArgs& fa, const vpt_atmosphere* sky, int n_passes, int sampled, int write_display, const PeerFrames* peers, cudaStream_t s);
+// flags: 64-bit epoch counters in peer-mapped memory.  signal: store `epoch` into slot `rank` of flag array `which` (0 ready, 1 done) of every
+// peer; wait: spin until slots 0..n-1 of the LOCAL array have all reached `epoch` (gives up after ~10 s and raises the block's error word).
+cudaError_t launch_peer_signal(unsigned long long* const peer_flags[kMaxPeers], int n, int rank, int which, unsigned long long epoch, cudaStream_t s);
+cudaError_t launch_peer_wait(unsigned long long* local_flags, int n, int which, unsigned long long epoch, cudaStream_t s);
+constexpr int kPeerFlagStride = 16;                   // u64 slots per flag array; layout of a block header: ready[16] done[16] error[1]
 // limit = min(W*H, 65536) entries are advanced (the reference updates entry y*W + x from pixel (x, y))
 cudaError_t launch_bn_prepare(void* bn, float2* table, int np, int limit, cudaStream_t s);
 cudaError_t launch_bn_advance(void* bn, int n, int limit, cudaStream_t s);

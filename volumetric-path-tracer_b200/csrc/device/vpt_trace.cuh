@@ -102,13 +102,7 @@ VPT_DEV void store_ray(const PV& pv, int s, const PathState& st)
 
 VPT_DEV void ray_rng_init(PathState& st, const FrameArgs& fa, uint32_t k)
 {
-    uint32_t idx = st.lp;
-    const FrameGeom& g = fa.geom;
-    if (g.n_ranks > 1) {
-        const uint32_t lr = st.lp / (uint32_t)g.width, x = st.lp - lr * (uint32_t)g.width;
-        idx = (uint32_t)global_row(g, (int)lr) * (uint32_t)g.width + x;
-    }
-    st.rng.init(idx, fa.kp.iteration + st.pass, k);
+    st.rng.init(ray_global_pixel(fa.geom, st.lp), fa.kp.iteration + st.pass, k);       // st.lp: the ray's pixel word (vpt_frame.cuh)
 }
 
 template <class PV>
@@ -347,7 +341,7 @@ VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, 
                 st.phase = PH_POINT_NEXT;
             } else {                                                // sphere branch tail (:1831-1833)
                 st.L += ld3(kp.sun_color) * kp.sun_mult * f3(tr) * fmaxf(dot(tc.sun_dir, st.aux), .0f) * st.beta;
-                if (fa.planeD) fa.planeD[(size_t)st.pass * fa.geom.n_local + st.lp] = make_float4(st.pos.x, st.pos.y, st.pos.z, 0.f);   // env_pos = ray_pos
+                if (fa.planeD) fa.planeD[(size_t)st.pass * fa.geom.n_local + ray_local_pixel(fa.geom, st.lp)] = make_float4(st.pos.x, st.pos.y, st.pos.z, 0.f);   // env_pos = ray_pos
                 st.sphere_bounced = true;
                 st.rd++; st.have_closest = false;
                 st.phase = PH_BOUNCE_TOP;
@@ -423,7 +417,7 @@ VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, 
 template <int kInteg>
 VPT_DEV void write_sample(const PathState& st, const FrameArgs& fa)
 {
-    const size_t o = (size_t)st.pass * fa.geom.n_local + st.lp;
+    const size_t o = (size_t)st.pass * fa.geom.n_local + ray_local_pixel(fa.geom, st.lp);
     fa.planeA[o] = make_float4(st.dir.x, st.dir.y, st.dir.z, st.alpha);                 // final direction, tr
     fa.planeB[o] = make_float4(st.L.x, st.L.y, st.L.z, st.depth);                       // L, depth
     fa.planeC[o] = make_float4(st.beta.x, st.beta.y, st.beta.z, 1.f);                   // beta

@@ -103,9 +103,99 @@ int comm_gather_frame(vpt_context* c, const FrameGeom& g, const void* d_local_ac
     return VPT_OK;
 }
 
+// ---- peer-memory exchange ---------------------------------------------------------------------------------------------------------
+static constexpr size_t kP2pHeader = 512;                      // ready[16] done[16] error[1] as u64
+static size_t p2p_accum_bytes(const vpt_context* c) { return (((size_t)c->p2p_w * c->p2p_h * 12) + 255) & ~(size_t)255; }
+static unsigned long long* p2p_flags(void* block) { return reinterpret_cast<unsigned long long*>(block); }
+
+int comm_p2p_begin(vpt_context* c, cudaStream_t stream) {
+    if (!c->p2p_on) return VPT_OK;
+    ++c->p2p_epoch;
+    unsigned long long* fl[kMaxPeers];
+    for (int p = 0; p < kMaxPeers; ++p) fl[p] = p < c->p2p_n ? p2p_flags(c->p2p_peer[p]) : nullptr;
+    VPT_CU(c, launch_peer_signal(fl, c->p2p_n, c->rank, 0, c->p2p_epoch, stream));     // "my frame of the previous call has been consumed"
+    c->launches++;
+    return VPT_OK;
+}
+
+int comm_p2p_peers(vpt_context* c, cudaStream_t stream, PeerFrames* out) {
+    *out = PeerFrames{};
+    if (!c->p2p_on) return VPT_OK;
+    VPT_CU(c, launch_peer_wait(p2p_flags(c->p2p_block), c->p2p_n, 0, c->p2p_epoch, stream));   // every peer has entered this call
+    c->launches++;
+    out->n = c->p2p_n;
+    for (int p = 0; p < c->p2p_n; ++p) {
+        char* base = reinterpret_cast<char*>(c->p2p_peer[p]);
+        out->accum[p] = reinterpret_cast<float*>(base + kP2pHeader);
+        out->display[p] = c->p2p_display ? reinterpret_cast<unsigned int*>(base + kP2pHeader + p2p_accum_bytes(c)) : nullptr;
+    }
+    return VPT_OK;
+}
+
+int comm_p2p_end(vpt_context* c, cudaStream_t stream) {
+    if (!c->p2p_on) return VPT_OK;
+    unsigned long long* fl[kMaxPeers];
+    for (int p = 0; p < kMaxPeers; ++p) fl[p] = p < c->p2p_n ? p2p_flags(c->p2p_peer[p]) : nullptr;
+    VPT_CU(c, launch_peer_signal(fl, c->p2p_n, c->rank, 1, c->p2p_epoch, stream));     // my stripes are in every frame ...
+    VPT_CU(c, launch_peer_wait(p2p_flags(c->p2p_block), c->p2p_n, 1, c->p2p_epoch, stream));   // ... and everybody's are in mine
+    c->launches += 2;
+    return VPT_OK;
+}
+
 } // namespace vpt
 
 extern "C" {
+
+int vpt_comm_p2p_export(vpt_context* c, int rank, int n_ranks, int stripe_rows, unsigned width, unsigned height, int with_display,
+                        unsigned char handle_out[VPT_P2P_HANDLE_BYTES]) {
+    if (!c || !handle_out || n_ranks < 1 || n_ranks > vpt::kMaxPeers || rank < 0 || rank >= n_ranks || stripe_rows < 1 || !width || !height)
+        return vpt::fail_ctx(c, VPT_ERR_INVALID, "vpt_comm_p2p_export: bad arguments (at most 8 ranks: one NVSwitch domain)");
+    if (c->p2p_block) return vpt::fail_ctx(c, VPT_ERR_INVALID, "vpt_comm_p2p_export: already exported");
+    static_assert(sizeof(cudaIpcMemHandle_t) == VPT_P2P_HANDLE_BYTES, "IPC handle size");
+    VPT_CU(c, cudaSetDevice(c->device));
+    int rc = vpt_set_partition(c, rank, n_ranks, stripe_rows);
+    if (rc != VPT_OK) return rc;
+    c->p2p_w = (int)width; c->p2p_h = (int)height; c->p2p_display = with_display != 0; c->p2p_n = n_ranks;
+    c->p2p_bytes = vpt::kP2pHeader + vpt::p2p_accum_bytes(c) + (with_display ? (size_t)width * height * 4 : 0);
+    VPT_CU(c, cudaMalloc(&c->p2p_block, c->p2p_bytes));
+    VPT_CU(c, cudaMemset(c->p2p_block, 0, c->p2p_bytes));
+    VPT_CU(c, cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    VPT_CU(c, cudaIpcGetMemHandle(&h, c->p2p_block));
+    memcpy(handle_out, &h, sizeof(h));
+    return VPT_OK;
+}
+
+int vpt_comm_p2p_import(vpt_context* c, const unsigned char* handles) {
+    if (!c || !handles || !c->p2p_block) return vpt::fail_ctx(c, VPT_ERR_INVALID, "vpt_comm_p2p_import: call vpt_comm_p2p_export first");
+    for (int p = 0; p < c->p2p_n; ++p) {
+        if (p == c->rank) { c->p2p_peer[p] = c->p2p_block; continue; }
+        cudaIpcMemHandle_t h; memcpy(&h, handles + (size_t)p * VPT_P2P_HANDLE_BYTES, sizeof(h));
+        VPT_CU(c, cudaIpcOpenMemHandle(&c->p2p_peer[p], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->p2p_on = true; c->p2p_epoch = 0;
+    return VPT_OK;
+}
+
+int vpt_comm_p2p_frame(vpt_context* c, vpt_devptr_t* d_full_accum, vpt_devptr_t* d_full_display) {
+    if (!c || !c->p2p_block) return vpt::fail_ctx(c, VPT_ERR_INVALID, "vpt_comm_p2p_frame: no exchange block");
+    char* base = reinterpret_cast<char*>(c->p2p_block);
+    if (d_full_accum) *d_full_accum = (vpt_devptr_t)(base + vpt::kP2pHeader);
+    if (d_full_display) *d_full_display = c->p2p_display ? (vpt_devptr_t)(base + vpt::kP2pHeader + vpt::p2p_accum_bytes(c)) : 0;
+    return VPT_OK;
+}
+
+int vpt_comm_p2p_enable(vpt_context* c, int on) {
+    if (!c || !c->p2p_block || !c->p2p_peer[c->rank]) return vpt::fail_ctx(c, VPT_ERR_INVALID, "vpt_comm_p2p_enable: exchange not set up");
+    c->p2p_on = on != 0;
+    return VPT_OK;
+}
+
+int vpt_comm_p2p_status(vpt_context* c, unsigned long long* timeouts) {
+    if (!c || !timeouts || !c->p2p_block) return vpt::fail_ctx(c, VPT_ERR_INVALID, "vpt_comm_p2p_status: no exchange block");
+    VPT_CU(c, cudaMemcpy(timeouts, vpt::p2p_flags(c->p2p_block) + 2 * vpt::kPeerFlagStride, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return VPT_OK;
+}
 
 int vpt_comm_get_unique_id(unsigned char id_out[VPT_COMM_ID_BYTES]) {
     if (!id_out) return vpt::fail_global(VPT_ERR_INVALID, "vpt_comm_get_unique_id: null argument");
@@ -168,6 +258,12 @@ int vpt_comm_destroy(vpt_context* c) {
     cudaFree(c->d_gathered); c->d_gathered = nullptr; c->cap_gathered = 0;
     cudaFree(c->d_gathered_disp); c->d_gathered_disp = nullptr; c->cap_gathered_disp = 0;
     c->d_full_accum = c->d_full_display = nullptr; c->gather_pending = false;
+    if (c->p2p_block) {
+        cudaDeviceSynchronize();
+        for (int p = 0; p < c->p2p_n; ++p) if (p != c->rank && c->p2p_peer[p]) cudaIpcCloseMemHandle(c->p2p_peer[p]);
+        cudaFree(c->p2p_block); c->p2p_block = nullptr; c->p2p_on = false; c->p2p_n = 0;
+        for (auto& q : c->p2p_peer) q = nullptr;
+    }
     return VPT_OK;
 }
 

@@ -49,6 +49,8 @@ vpt::FrameGeom vpt::make_frame_geom(const vpt_context* c, unsigned w, unsigned h
         g.local_rows = per_rank * g.stripe_h;
     }
     g.n_local = g.local_rows * g.width;
+    g.stripe_shift = -1;
+    for (int sh = 0; sh < 16; ++sh) if ((1 << sh) == g.stripe_h) g.stripe_shift = sh;
     return g;
 }
 
@@ -200,6 +202,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
     // environment_type == 0: the caller's AtmosphereParameters (scalars + the four precomputed look-up textures)
     vpt_atmosphere atmo;
     memcpy(&atmo, params[VPT_ARG_ATMOSPHERE], sizeof(vpt_atmosphere));
+    if (c->n_ranks > 1 && (kp.resolution.x > 65535u || kp.resolution.y > 65535u)) return fail(c, VPT_ERR_UNSUPPORTED, "a partitioned frame is limited to 65535 x 65535 pixels");
     const bool vol_integ = (kp.integrator != 0);             // vol_integrator always ends on the precomputed sky (:1752)
     const bool sky_env = (kp.environment_type == 0) || vol_integ;
     const bool samples = kp.render && kp.iteration < kp.max_interactions;
@@ -338,6 +341,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         c->events.push_back(ev);
         return e;
     };
+    { int rc = vpt::comm_p2p_begin(c, stream); if (rc != VPT_OK) return rc; }      // multi-GPU peer exchange: this rank's frame may be overwritten from here on
     const uint32_t it0 = kp.iteration;
     const unsigned long long frame_px = (unsigned long long)kp.resolution.x * kp.resolution.y;
     const int bn_limit = frame_px < 65536ull ? (int)frame_px : 65536;
@@ -352,7 +356,9 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         else VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, vol_integ ? &atmo : nullptr, lean, slots, trace_ctas, stream); }));
         const bool last = (done + np == n_passes);
         if (c->gather_pending) { int rc = vpt::comm_before_accum_write(c, stream); if (rc != VPT_OK) return rc; }
-        VPT_CUDA(c, timed(2, [&] { return vpt::launch_resolve(fa, sky, (int)np, 1, last ? 1 : 0, stream); }));
+        vpt::PeerFrames peers;
+        if (last) { int rc = vpt::comm_p2p_peers(c, stream, &peers); if (rc != VPT_OK) return rc; }
+        VPT_CUDA(c, timed(2, [&] { return vpt::launch_resolve(fa, sky, (int)np, 1, last ? 1 : 0, last ? &peers : nullptr, stream); }));
         c->launches += 4;
         done += np;
     }
@@ -360,11 +366,15 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         // passes that no longer sample: WHITE / re-tonemap semantics of the kernel tail
         fa.kp.iteration = it0 + n_sampled;
         if (c->gather_pending) { int rc = vpt::comm_before_accum_write(c, stream); if (rc != VPT_OK) return rc; }
-        VPT_CUDA(c, vpt::launch_resolve(fa, sky, (int)(n_passes - n_sampled), 0, 1, stream));
+        vpt::PeerFrames peers;
+        { int rc = vpt::comm_p2p_peers(c, stream, &peers); if (rc != VPT_OK) return rc; }
+        VPT_CUDA(c, vpt::launch_resolve(fa, sky, (int)(n_passes - n_sampled), 0, 1, &peers, stream));
         VPT_CUDA(c, vpt::launch_bn_advance((void*)kp.blue_noise_buffer, (int)(n_passes - n_sampled), bn_limit, stream));
         c->launches += 2;
     }
-    // multi-GPU: the one collective of the path -- all-gather of the rank-local frame into the caller's full-frame buffers
+    // multi-GPU: the one exchange of the path.  Peer-memory mode: the last resolve above already stored every pixel into every rank's
+    // frame; publish and wait for the peers.  NCCL mode: all-gather of the rank-local frame into the caller's full-frame buffers.
+    { int rc = vpt::comm_p2p_end(c, stream); if (rc != VPT_OK) return rc; }
     if (c->nccl_comm && (c->d_full_accum || c->d_full_display)) {
         int rc = vpt::comm_gather_frame(c, fa.geom, (const void*)kp.accum_buffer, (const void*)kp.display_buffer, stream);
         if (rc != VPT_OK) return rc;

@@ -56,6 +56,10 @@ struct vpt_context {
     void*  d_full_display = nullptr;                            // caller-owned full frame u32 [H][W], may be null
     void*  d_gathered_disp = nullptr; size_t cap_gathered_disp = 0;
     cudaStream_t comm_stream = nullptr; cudaEvent_t ev_render_done = nullptr, ev_gather_done = nullptr;
+    // peer-memory exchange (vpt_comm_p2p_*): one cudaMalloc'd block per rank {flags, full accum, full display}, IPC-mapped into every rank
+    void*  p2p_block = nullptr; size_t p2p_bytes = 0; int p2p_w = 0, p2p_h = 0;
+    void*  p2p_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [rank] -> that rank's block as mapped here (own: p2p_block)
+    int    p2p_n = 0; bool p2p_on = false, p2p_display = false; unsigned long long p2p_epoch = 0;
     int    gather_async = 0;                                    // option "gather_async": gather on the side stream (see vpt_comm_wait)
     bool   gather_pending = false;
     size_t max_scratch_bytes = (size_t)12 << 30;                // cap of the per-chunk ray queue + sample planes
@@ -99,6 +103,9 @@ int  fail_global(int code, const std::string& msg);     // records the text for 
 int  fail_ctx(vpt_context* ctx, int code, const std::string& msg);
 FrameGeom make_frame_geom(const vpt_context* c, unsigned w, unsigned h);
 // after the last resolve of a vpt_render_passes call: all-gather + un-permute into the caller's full-frame buffers (vpt_comm.cpp)
+int  comm_p2p_begin(vpt_context* c, cudaStream_t stream);                                        // call start: tell the peers this rank's frame may be overwritten
+int  comm_p2p_peers(vpt_context* c, cudaStream_t stream, PeerFrames* out);                       // before the call's last resolve: wait for the peers, hand out their frames
+int  comm_p2p_end(vpt_context* c, cudaStream_t stream);                                          // after it: publish, and wait until every peer has published
 int  comm_gather_frame(vpt_context* c, const FrameGeom& g, const void* d_local_accum, const void* d_local_display, cudaStream_t stream);
 int  comm_before_accum_write(vpt_context* c, cudaStream_t stream);   // async mode: the previous gather must have read accum
 

@@ -137,24 +137,54 @@ class Renderer:
             lib.vpt_destroy(self.ctx); self.ctx = C.c_void_p(0)
 
 
+class _DeviceView:
+    """Zero-copy torch view of library-owned device memory (__cuda_array_interface__)."""
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
 class DistributedRenderer:
     """Frame sharded over the ranks of a torch.distributed job (one process per GPU); scene replicated on each.
 
-    torch.distributed is only the BOOTSTRAP here (it carries the 128-byte NCCL id from rank 0 to the others); the exchange
-    itself -- one ncclAllGather of the rank-local accumulators per render call + the stripe un-permutation -- is issued by the
-    C++ library behind the last kernel of the call (vpt_comm_*).  Pixels are independent and every Philox stream is keyed by
-    the GLOBAL pixel index, so the gathered frame is bit-identical to a single-GPU render whatever the partition."""
+    torch.distributed is only the BOOTSTRAP here: it carries the 64-byte IPC handles (exchange="p2p") or the 128-byte NCCL id
+    (exchange="nccl") between the ranks.  The exchange itself is the C++ library's:
+      * "p2p" (default, up to 8 GPUs of one NVSwitch domain): the last resolve kernel of a render call stores every finished pixel
+        straight into every rank's full frame over peer mappings -- gather and stripe un-permutation fused into the producer;
+      * "nccl": one ncclAllGather of the rank-local accumulators + an un-permutation kernel behind the last kernel of the call.
+    Pixels are independent and every Philox stream is keyed by the GLOBAL pixel index, so the gathered frame is bit-identical to a
+    single-GPU render whatever the partition."""
 
-    def __init__(self, scene: Scene, width, height, cam=None, kp=None, stripe_rows=16, options=None, gather_display=False):
+    def __init__(self, scene: Scene, width, height, cam=None, kp=None, stripe_rows=16, options=None, gather_display=False, exchange="p2p"):
         import torch.distributed as dist
         self.dist = dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if self.world > 8 and exchange == "p2p": exchange = "nccl"
+        self.exchange = exchange if self.world > 1 else "none"
         self.r = Renderer(scene, width, height, cam=cam, kp=kp, rank=self.rank, n_ranks=self.world,
                           stripe_rows=stripe_rows, options=options)
-        self.full = torch.zeros(self.r.height * self.r.width, 3, dtype=torch.float32, device=scene.device)
-        self.full_display = torch.zeros(self.r.height * self.r.width, dtype=torch.int32, device=scene.device) if gather_display else None
+        n_px = self.r.height * self.r.width
+        self.full = None; self.full_display = None
         self.collective_note = "none (1 rank)"
-        if self.world > 1:
+        if self.world > 1 and self.exchange == "p2p":
+            raw = (C.c_ubyte * 64)()
+            check(lib.vpt_comm_p2p_export(self.r.ctx, self.rank, self.world, stripe_rows, self.r.width, self.r.height, 1 if gather_display else 0, raw),
+                  self.r.ctx, "vpt_comm_p2p_export")
+            mine = torch.tensor(list(raw), dtype=torch.uint8, device=scene.device)
+            allh = [torch.zeros(64, dtype=torch.uint8, device=scene.device) for _ in range(self.world)]
+            dist.all_gather(allh, mine)                                        # bootstrap only
+            blob = (C.c_ubyte * (64 * self.world))(*torch.cat(allh).cpu().tolist())
+            check(lib.vpt_comm_p2p_import(self.r.ctx, blob), self.r.ctx, "vpt_comm_p2p_import")
+            pa, pd = C.c_uint64(0), C.c_uint64(0)
+            check(lib.vpt_comm_p2p_frame(self.r.ctx, C.byref(pa), C.byref(pd)), self.r.ctx, "vpt_comm_p2p_frame")
+            self.full = torch.as_tensor(_DeviceView(pa.value, (n_px, 3), "<f4"), device=scene.device)
+            if gather_display: self.full_display = torch.as_tensor(_DeviceView(pd.value, (n_px,), "<i4"), device=scene.device)
+            dist.barrier()                                                     # every rank has mapped every block before the first exchange
+            self.collective_note = ("peer-memory exchange: the last resolve kernel stores each pixel into every rank's frame over NVLink peer mappings "
+                                    "(all-gather + un-permutation fused into the producer), two flag exchanges per call; no NCCL on the data path")
+        else:
+            self.full = torch.zeros(n_px, 3, dtype=torch.float32, device=scene.device)
+            self.full_display = torch.zeros(n_px, dtype=torch.int32, device=scene.device) if gather_display else None
+        if self.world > 1 and self.exchange == "nccl":
             idb = torch.zeros(128, dtype=torch.uint8)
             if self.rank == 0:
                 raw = (C.c_ubyte * 128)()
@@ -163,21 +193,37 @@ class DistributedRenderer:
             idb = idb.to(scene.device); dist.broadcast(idb, src=0)          # bootstrap only
             raw = (C.c_ubyte * 128)(*idb.cpu().tolist())
             check(lib.vpt_comm_init(self.r.ctx, raw, self.rank, self.world, stripe_rows), self.r.ctx, "vpt_comm_init")
-            check(lib.vpt_comm_set_gather(self.r.ctx, C.c_void_p(self.full.data_ptr()),
-                                          C.c_void_p(self.full_display.data_ptr()) if gather_display else None), self.r.ctx, "vpt_comm_set_gather")
+            self.set_gather(True)
             v = C.c_int(0); lib.vpt_comm_info(self.r.ctx, C.byref(v), None, None)
             self.collective_note = (f"1 ncclAllGather (NCCL {v.value}) of the float3 accumulators per step, issued by libvpt_b200.so behind the last "
                                     "resolve kernel, + stripe un-permutation kernel")
 
     def render(self, n_passes, stream=None):
-        self.r.render(n_passes, stream=stream)                               # the gather is part of the call
+        self.r.render(n_passes, stream=stream)                               # the exchange is part of the call
         if self.world == 1:
             self.full.copy_(self.r.buffers.accum)
+            if self.full_display is not None: self.full_display.copy_(self.r.buffers.display)
+
+    def set_gather(self, enabled: bool):
+        """Switch the per-call exchange off (rank-local work only: profiling runs that not every rank takes part in) or back on."""
+        if self.world == 1: return
+        if self.exchange == "p2p":
+            check(lib.vpt_comm_p2p_enable(self.r.ctx, 1 if enabled else 0), self.r.ctx, "vpt_comm_p2p_enable")
+        elif enabled:
+            check(lib.vpt_comm_set_gather(self.r.ctx, C.c_void_p(self.full.data_ptr()),
+                                          C.c_void_p(self.full_display.data_ptr()) if self.full_display is not None else None), self.r.ctx, "vpt_comm_set_gather")
+        else:
+            check(lib.vpt_comm_set_gather(self.r.ctx, None, None), self.r.ctx, "vpt_comm_set_gather")
+
+    def abandoned_waits(self):
+        if self.exchange != "p2p": return 0
+        n = C.c_uint64(0); check(lib.vpt_comm_p2p_status(self.r.ctx, C.byref(n)), self.r.ctx, "vpt_comm_p2p_status"); return int(n.value)
 
     def full_accum(self):
         return self.full.view(self.r.height, self.r.width, 3)
 
     def close(self):
+        self.full = None; self.full_display = None
         self.r.close()
 
 
