@@ -427,8 +427,9 @@ def main():
             tpath = os.path.join(ROOT, "profiles", name)
             if os.path.exists(tpath):
                 tj = json.load(open(tpath))
-                if tj.get("passes_per_launch") == opts.get("passes_per_chunk", 32) and world == 1 and args.config == tj.get("baseline_config", 2):
-                    traffic = tj["k_trace_dram_bytes_per_launch"]
+                ent = tj if args.config == tj.get("baseline_config", 2) else tj.get("configs", {}).get(str(args.config))
+                if ent and not args.fast and world == 1 and ent.get("passes_per_launch") == (opts.get("passes_per_chunk") or 32):
+                    traffic = ent["k_trace_dram_bytes_per_launch"]
                 break
         bytes_per_sample = 88.0 + 32.0 * lookups_per_sample          # framebuffer stream + 32 B per density lookup
         step_gbs = value * bytes_per_sample / 1e3
@@ -441,8 +442,10 @@ def main():
                     "kernel_ms_per_step": {k: v["ms"] / n_steps_prof for k, v in kt.items()}, "kernel_ms_per_step_by_rank": per_rank_ms,
                     "step": {"bytes_per_sample": bytes_per_sample, "achieved": step_gbs, "achieved_per_gpu": step_gbs / world, "frac": step_gbs / world / peak,
                              "note": "whole step charged with SURVEY 8(d)'s 88 B + 32 B x lookups per sample; per-GPU rate over one GPU's peak"},
-                    "note": "dragon.vdb is 425 KB: volume lookups are served by L1/TEX/L2, DRAM only sees the ray queue and the sample planes; "
-                            "the path is bound by latency / instruction issue, not HBM (SURVEY 8(d)); see profiles/"}
+                    "note": ("4 GiB grid, nothing cache-resident: every look-up is a DRAM round trip (152 B of sector traffic for 32 algorithmic bytes); "
+                             "the kernel is bound by memory LATENCY (ncu: 44 % of DRAM throughput, 40 % long-scoreboard stalls); see profiles/r02_cfg4_*") if args.config == 4 else
+                            ("the volume is L2-resident (dragon.vdb: 425 KB): look-ups are served by L1/TEX/L2, DRAM only sees the ray queue and the sample planes; "
+                             "the path is bound by latency / instruction issue, not HBM (SURVEY 8(d)); see profiles/")}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config in (1, 2):      # N = 1 only

@@ -291,7 +291,9 @@ def test_scene_cache_survives_address_reuse(dragon):
 
 # ---- multi-GPU: gathered frame == single-GPU frame, bit for bit ---------------------------------------------------------
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on the box")
-def test_two_rank_nccl_gather_is_bitwise_identical():
+def test_two_rank_exchange_is_bitwise_identical():
+    """tools/mgpu_check.py under torchrun on 2 GPUs: peer-memory exchange and NCCL gather, accumulators and display words, two consecutive
+    frames, side-stream gather -- each equal to the single-GPU frame bit for bit."""
     env = dict(os.environ); env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tools", "mgpu_check.py")]

@@ -387,9 +387,10 @@ __global__ void k_peer_wait(unsigned long long* local, int n, int which, unsigne
 // itself is left advanced by `np` passes.  One launch replaces the per-thread replay in k_generate.
 // `limit` = min(W*H, 65536): the reference advances entry idx = y*W + x from the thread of pixel (x, y), so a frame of fewer than
 // 65536 pixels leaves the entries beyond W*H untouched (they are still READ as jitter through (y % 256) * 256 + x % 256).
-__global__ void k_bn_prepare(float3* bn, float2* table, int np, int limit)
+__global__ void k_bn_prepare(float3* bn, float2* table, int np, int limit, unsigned* queue_counters)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0 && queue_counters) { queue_counters[0] = 0u; queue_counters[1] = 0u; }   // first kernel of a round: also resets the ray queue (count, head)
     if (idx >= 256 * 256) return;
     float3 val = bn[idx];
     if (idx >= limit) {
@@ -554,9 +555,9 @@ cudaError_t launch_peer_wait(unsigned long long* local_flags, int n, int which, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_bn_prepare(void* bn, float2* table, int np, int limit, cudaStream_t s)
+cudaError_t launch_bn_prepare(void* bn, float2* table, int np, int limit, unsigned* queue_counters, cudaStream_t s)
 {
-    k_bn_prepare<<<256, 256, 0, s>>>(reinterpret_cast<float3*>(bn), table, np, limit);
+    k_bn_prepare<<<256, 256, 0, s>>>(reinterpret_cast<float3*>(bn), table, np, limit, queue_counters);
     return cudaGetLastError();
 }
 

@@ -75,7 +75,7 @@ cudaError_t launch_peer_signal(unsigned long long* const peer_flags[kMaxPeers], 
 cudaError_t launch_peer_wait(unsigned long long* local_flags, int n, int which, unsigned long long epoch, cudaStream_t s);
 constexpr int kPeerFlagStride = 16;                   // u64 slots per flag array; layout of a block header: ready[16] done[16] error[1]
 // limit = min(W*H, 65536) entries are advanced (the reference updates entry y*W + x from pixel (x, y))
-cudaError_t launch_bn_prepare(void* bn, float2* table, int np, int limit, cudaStream_t s);
+cudaError_t launch_bn_prepare(void* bn, float2* table, int np, int limit, unsigned* queue_counters, cudaStream_t s);   // also zeroes queue_counters[0..1]
 cudaError_t launch_bn_advance(void* bn, int n, int limit, cudaStream_t s);
 cudaError_t launch_unpermute(const void* gathered, void* full, const FrameGeom& g, int elem_bytes, cudaStream_t s);
 

@@ -349,8 +349,7 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
     while (done < n_sampled) {
         const unsigned np = (n_sampled - done) < (unsigned)chunk ? (n_sampled - done) : (unsigned)chunk;
         fa.kp.iteration = it0 + done;
-        VPT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned) * 2, stream));
-        VPT_CUDA(c, timed(3, [&] { return vpt::launch_bn_prepare((void*)kp.blue_noise_buffer, c->d_bn_table, (int)np, bn_limit, stream); }));   // jitter table + advance
+        VPT_CUDA(c, timed(3, [&] { return vpt::launch_bn_prepare((void*)kp.blue_noise_buffer, c->d_bn_table, (int)np, bn_limit, c->d_counters, stream); }));   // jitter table + advance + queue reset
         VPT_CUDA(c, timed(0, [&] { return vpt::launch_generate(fa, (int)np, stream); }));
         if (c->brick_pool) VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace_brick(fa, c->brick_pool, c->brick_dims, trace_ctas, stream); }));
         else VPT_CUDA(c, timed(1, [&] { return vpt::launch_trace(fa, vol_integ ? &atmo : nullptr, lean, slots, trace_ctas, stream); }));

@@ -166,19 +166,34 @@ class DistributedRenderer:
         self.full = None; self.full_display = None
         self.collective_note = "none (1 rank)"
         if self.world > 1 and self.exchange == "p2p":
+            # set-up can fail on one rank only (no peer access between two devices, IPC disabled in a container): every rank reports, and
+            # all of them fall back to NCCL together
+            ok, err = 1, ""
             raw = (C.c_ubyte * 64)()
-            check(lib.vpt_comm_p2p_export(self.r.ctx, self.rank, self.world, stripe_rows, self.r.width, self.r.height, 1 if gather_display else 0, raw),
-                  self.r.ctx, "vpt_comm_p2p_export")
+            try:
+                check(lib.vpt_comm_p2p_export(self.r.ctx, self.rank, self.world, stripe_rows, self.r.width, self.r.height, 1 if gather_display else 0, raw),
+                      self.r.ctx, "vpt_comm_p2p_export")
+            except N.VptError as e:
+                ok, err = 0, str(e)
             mine = torch.tensor(list(raw), dtype=torch.uint8, device=scene.device)
             allh = [torch.zeros(64, dtype=torch.uint8, device=scene.device) for _ in range(self.world)]
             dist.all_gather(allh, mine)                                        # bootstrap only
-            blob = (C.c_ubyte * (64 * self.world))(*torch.cat(allh).cpu().tolist())
-            check(lib.vpt_comm_p2p_import(self.r.ctx, blob), self.r.ctx, "vpt_comm_p2p_import")
+            if ok:
+                blob = (C.c_ubyte * (64 * self.world))(*torch.cat(allh).cpu().tolist())
+                try:
+                    check(lib.vpt_comm_p2p_import(self.r.ctx, blob), self.r.ctx, "vpt_comm_p2p_import")
+                except N.VptError as e:
+                    ok, err = 0, str(e)
+            flag = torch.tensor([ok], dtype=torch.int32, device=scene.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)                        # also: every rank has mapped every block before the first exchange
+            if int(flag.item()) == 0:
+                if ok: lib.vpt_comm_p2p_enable(self.r.ctx, 0)
+                self.exchange = "nccl"; self.p2p_error = err or "another rank could not set up the peer mappings"
+        if self.world > 1 and self.exchange == "p2p":
             pa, pd = C.c_uint64(0), C.c_uint64(0)
             check(lib.vpt_comm_p2p_frame(self.r.ctx, C.byref(pa), C.byref(pd)), self.r.ctx, "vpt_comm_p2p_frame")
             self.full = torch.as_tensor(_DeviceView(pa.value, (n_px, 3), "<f4"), device=scene.device)
             if gather_display: self.full_display = torch.as_tensor(_DeviceView(pd.value, (n_px,), "<i4"), device=scene.device)
-            dist.barrier()                                                     # every rank has mapped every block before the first exchange
             self.collective_note = ("peer-memory exchange: the last resolve kernel stores each pixel into every rank's frame over NVLink peer mappings "
                                     "(all-gather + un-permutation fused into the producer), two flag exchanges per call; no NCCL on the data path")
         else:
