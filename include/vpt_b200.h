@@ -93,6 +93,10 @@ int  vpt_comm_destroy(vpt_context* ctx);
 int  vpt_comm_p2p_export(vpt_context* ctx, int rank, int n_ranks, int stripe_rows, unsigned width, unsigned height, int with_display,
                          unsigned char handle_out[VPT_P2P_HANDLE_BYTES]);
 int  vpt_comm_p2p_import(vpt_context* ctx, const unsigned char* handles /* n_ranks x VPT_P2P_HANDLE_BYTES, rank order */);
+/* Same-process peers (one process driving several contexts -- several GPUs with peer access enabled, or several shards on one GPU on
+ * separate streams): exchange the block addresses (vpt_comm_p2p_block) instead of IPC handles. */
+int  vpt_comm_p2p_block(vpt_context* ctx, vpt_devptr_t* d_block);
+int  vpt_comm_p2p_import_local(vpt_context* ctx, const vpt_devptr_t* blocks /* n_ranks addresses, rank order */);
 int  vpt_comm_p2p_frame(vpt_context* ctx, vpt_devptr_t* d_full_accum_f3, vpt_devptr_t* d_full_display_u32);
 int  vpt_comm_p2p_enable(vpt_context* ctx, int on);
 int  vpt_comm_p2p_status(vpt_context* ctx, unsigned long long* abandoned_waits);

@@ -302,6 +302,49 @@ def test_two_rank_exchange_is_bitwise_identical():
     assert out.returncode == 0 and "BITWISE_OK" in out.stdout
 
 
+def test_peer_memory_exchange_with_three_shards_on_one_gpu(dragon):
+    """The multi-GPU exchange protocol on ONE device: three contexts render the three shards of a frame on three streams and exchange
+    through each other's blocks (same-process peer import).  The last resolve kernel of every shard stores its pixels into all three
+    frames between the two flag handshakes; every frame must equal the single-context frame bit for bit, twice in a row (the second
+    call exercises the "previous frame consumed" handshake), display words included."""
+    W, H, P, R = 640, 360, 3, 3
+    one_scene = make_scene(dragon)
+    one = V.Renderer(one_scene, W, H, kp=make_kp(ray_depth=3))
+    one.render(P); torch.cuda.synchronize()
+    want1 = one.buffers.accum.clone(); disp1 = one.buffers.display.clone()
+    one.kp.iteration = 0; one.render(P); torch.cuda.synchronize()
+    want2 = one.buffers.accum.clone()
+    scenes = [make_scene(dragon) for _ in range(R)]                    # one blue-noise state per shard, as one per process
+    rs = [V.Renderer(scenes[k], W, H, kp=make_kp(ray_depth=3), cam=one.cam, rank=k, n_ranks=R, stripe_rows=8) for k in range(R)]
+    blocks = (C.c_uint64 * R)()
+    for k, r in enumerate(rs):
+        raw = (C.c_ubyte * 64)()
+        V._native.check(V.lib.vpt_comm_p2p_export(r.ctx, k, R, 8, W, H, 1, raw), r.ctx, "vpt_comm_p2p_export")
+        b = C.c_uint64(0); V._native.check(V.lib.vpt_comm_p2p_block(r.ctx, C.byref(b)), r.ctx, "vpt_comm_p2p_block"); blocks[k] = b.value
+    frames = []
+    for r in rs:
+        V._native.check(V.lib.vpt_comm_p2p_import_local(r.ctx, blocks), r.ctx, "vpt_comm_p2p_import_local")
+        pa, pd = C.c_uint64(0), C.c_uint64(0)
+        V._native.check(V.lib.vpt_comm_p2p_frame(r.ctx, C.byref(pa), C.byref(pd)), r.ctx, "vpt_comm_p2p_frame")
+        frames.append((torch.as_tensor(V.renderer._DeviceView(pa.value, (W * H, 3), "<f4"), device="cuda"),
+                       torch.as_tensor(V.renderer._DeviceView(pd.value, (W * H,), "<i4"), device="cuda")))
+    streams = [torch.cuda.Stream() for _ in range(R)]
+    torch.cuda.synchronize()
+    for want, check_display in ((want1, True), (want2, False)):
+        for r, st in zip(rs, streams):
+            r.kp.iteration = 0
+            r.render(P, stream=st.cuda_stream)                          # asynchronous: the three calls overlap on the device
+        torch.cuda.synchronize()
+        for k, (fa, fd) in enumerate(frames):
+            assert torch.equal(fa, want), f"frame held by shard {k}"
+            if check_display: assert torch.equal(fd, disp1.view(torch.int32) if disp1.dtype != torch.int32 else disp1), f"display held by shard {k}"
+    for r in rs:
+        n = C.c_uint64(0); V._native.check(V.lib.vpt_comm_p2p_status(r.ctx, C.byref(n)), r.ctx, "vpt_comm_p2p_status")
+        assert n.value == 0, "a flag wait was abandoned"
+    frames.clear()
+    for r in rs: r.close()
+
+
 # ---- level (A): the single-entry module behind the reference's unchanged Driver-API loader ------------------------------------
 LEVEL_A = os.path.join(os.path.dirname(V.LIB_PATH), "volume_rt_kernel_b200.cubin")
 

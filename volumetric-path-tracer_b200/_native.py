@@ -156,7 +156,7 @@ EXPORTED_SYMBOLS = [
     "vpt_comm_get_unique_id", "vpt_comm_init", "vpt_comm_set_gather", "vpt_comm_wait", "vpt_comm_info", "vpt_comm_destroy",
     "vpt_texture_create_3d_from_device", "vpt_procedural_fill", "vpt_bricks_create", "vpt_bricks_destroy", "vpt_set_brick_volume", "vpt_bricks_read", "vpt_debug_sampler_compare", "vpt_atmosphere_options_defaults", "vpt_atmosphere_precompute", "vpt_atmosphere_destroy",
     "vpt_texture_read_f4", "vpt_debug_texture_sample",
-    "vpt_comm_p2p_export", "vpt_comm_p2p_import", "vpt_comm_p2p_frame", "vpt_comm_p2p_enable", "vpt_comm_p2p_status",
+    "vpt_comm_p2p_export", "vpt_comm_p2p_import", "vpt_comm_p2p_import_local", "vpt_comm_p2p_block", "vpt_comm_p2p_frame", "vpt_comm_p2p_enable", "vpt_comm_p2p_status",
 ]
 
 # ---- prototypes ------------------------------------------------------------------------------------
@@ -197,6 +197,8 @@ lib.vpt_comm_info.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POI
 lib.vpt_comm_destroy.argtypes = [_vp]; lib.vpt_comm_destroy.restype = C.c_int
 lib.vpt_comm_p2p_export.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, C.POINTER(C.c_ubyte)]; lib.vpt_comm_p2p_export.restype = C.c_int
 lib.vpt_comm_p2p_import.argtypes = [_vp, C.POINTER(C.c_ubyte)]; lib.vpt_comm_p2p_import.restype = C.c_int
+lib.vpt_comm_p2p_import_local.argtypes = [_vp, C.POINTER(C.c_uint64)]; lib.vpt_comm_p2p_import_local.restype = C.c_int
+lib.vpt_comm_p2p_block.argtypes = [_vp, C.POINTER(C.c_uint64)]; lib.vpt_comm_p2p_block.restype = C.c_int
 lib.vpt_comm_p2p_frame.argtypes = [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]; lib.vpt_comm_p2p_frame.restype = C.c_int
 lib.vpt_comm_p2p_enable.argtypes = [_vp, C.c_int]; lib.vpt_comm_p2p_enable.restype = C.c_int
 lib.vpt_comm_p2p_status.argtypes = [_vp, C.POINTER(C.c_uint64)]; lib.vpt_comm_p2p_status.restype = C.c_int

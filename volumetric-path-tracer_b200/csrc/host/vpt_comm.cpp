@@ -177,6 +177,22 @@ int vpt_comm_p2p_import(vpt_context* c, const unsigned char* handles) {
     return VPT_OK;
 }
 
+int vpt_comm_p2p_import_local(vpt_context* c, const vpt_devptr_t* blocks) {
+    if (!c || !blocks || !c->p2p_block) return vpt::fail_ctx(c, VPT_ERR_INVALID, "vpt_comm_p2p_import_local: call vpt_comm_p2p_export first");
+    for (int p = 0; p < c->p2p_n; ++p) {
+        if (p != c->rank && !blocks[p]) return vpt::fail_ctx(c, VPT_ERR_INVALID, "vpt_comm_p2p_import_local: null block");
+        c->p2p_peer[p] = p == c->rank ? c->p2p_block : reinterpret_cast<void*>(blocks[p]);
+    }
+    c->p2p_local = true; c->p2p_on = true; c->p2p_epoch = 0;
+    return VPT_OK;
+}
+
+int vpt_comm_p2p_block(vpt_context* c, vpt_devptr_t* d_block) {
+    if (!c || !d_block || !c->p2p_block) return vpt::fail_ctx(c, VPT_ERR_INVALID, "vpt_comm_p2p_block: no exchange block");
+    *d_block = (vpt_devptr_t)c->p2p_block;
+    return VPT_OK;
+}
+
 int vpt_comm_p2p_frame(vpt_context* c, vpt_devptr_t* d_full_accum, vpt_devptr_t* d_full_display) {
     if (!c || !c->p2p_block) return vpt::fail_ctx(c, VPT_ERR_INVALID, "vpt_comm_p2p_frame: no exchange block");
     char* base = reinterpret_cast<char*>(c->p2p_block);
@@ -260,7 +276,7 @@ int vpt_comm_destroy(vpt_context* c) {
     c->d_full_accum = c->d_full_display = nullptr; c->gather_pending = false;
     if (c->p2p_block) {
         cudaDeviceSynchronize();
-        for (int p = 0; p < c->p2p_n; ++p) if (p != c->rank && c->p2p_peer[p]) cudaIpcCloseMemHandle(c->p2p_peer[p]);
+        if (!c->p2p_local) for (int p = 0; p < c->p2p_n; ++p) if (p != c->rank && c->p2p_peer[p]) cudaIpcCloseMemHandle(c->p2p_peer[p]);
         cudaFree(c->p2p_block); c->p2p_block = nullptr; c->p2p_on = false; c->p2p_n = 0;
         for (auto& q : c->p2p_peer) q = nullptr;
     }

@@ -59,7 +59,7 @@ struct vpt_context {
     // peer-memory exchange (vpt_comm_p2p_*): one cudaMalloc'd block per rank {flags, full accum, full display}, IPC-mapped into every rank
     void*  p2p_block = nullptr; size_t p2p_bytes = 0; int p2p_w = 0, p2p_h = 0;
     void*  p2p_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [rank] -> that rank's block as mapped here (own: p2p_block)
-    int    p2p_n = 0; bool p2p_on = false, p2p_display = false; unsigned long long p2p_epoch = 0;
+    int    p2p_n = 0; bool p2p_on = false, p2p_display = false, p2p_local = false; unsigned long long p2p_epoch = 0;
     int    gather_async = 0;                                    // option "gather_async": gather on the side stream (see vpt_comm_wait)
     bool   gather_pending = false;
     size_t max_scratch_bytes = (size_t)12 << 30;                // cap of the per-chunk ray queue + sample planes
