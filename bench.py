@@ -207,6 +207,7 @@ def main():
     ap.add_argument("--ref-jit61", action="store_true", help="with --impl reference: load the reference kernel as compute_61 PTX (its shipped form) and let the driver JIT it")
     ap.add_argument("--level-a", action="store_true", help="time the level (A) module: volume_rt_kernel_b200.cubin loaded and launched through the "
                     "Driver API exactly like the reference kernel (one launch + synchronize per spp), instead of the wavefront library")
+    ap.add_argument("--cells", action="store_true", help="config 4: trace from the cell table (8 corner texels per cell = one 32-byte sector per look-up, software filter) instead of the 3-D texture")
     ap.add_argument("--fast", action="store_true", help="config 4: trace from the brick pool (TMA-staged software sampler) instead of the 3-D texture")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -310,7 +311,11 @@ def main():
     if args.fast:
         if "volume" not in wl: raise SystemExit("--fast needs a workload with a procedural volume (--config 4)")
         r.set_brick_volume(wl["volume"])
-        config["trace_mode"] = f"fast: brick pool ({wl['volume'].brick_bytes / 2 ** 30:.2f} GiB) staged by cp.async.bulk, software 8-bit-weight trilinear; statistical parity"
+        config["trace_mode"] = f"brick pool ({wl['volume'].brick_bytes / 2 ** 30:.2f} GiB) staged by cp.async.bulk (TMA), the texture unit's filter in software"
+    elif args.cells:
+        if "volume" not in wl: raise SystemExit("--cells needs a workload with a procedural volume (--config 4)")
+        r.set_cell_volume(wl["volume"])
+        config["trace_mode"] = f"cell table ({wl['volume'].cell_bytes / 2 ** 30:.2f} GiB: 32 B = one sector per look-up), the texture unit's filter in software"
     else:
         config["trace_mode"] = "parity: tex3D (bit-exact per seed)"
     l0, _ = r.stats()
@@ -355,6 +360,7 @@ def main():
                 scene.reset_blue_noise()
                 one = V.Renderer(scene, WIDTH, HEIGHT, kp=_copy_kp(V, kp), cam=r.cam, options=opts)
                 if args.fast: one.set_brick_volume(wl["volume"])
+                if args.cells: one.set_cell_volume(wl["volume"])
                 one.render(SPP, stream=stream); torch.cuda.synchronize()
                 parity["gathered_equals_single_gpu_bitwise"] = bool(torch.equal(full, one.buffers.accum))
                 parity_fail |= not parity["gathered_equals_single_gpu_bitwise"]
@@ -371,8 +377,7 @@ def main():
                 scene.reset_blue_noise(); orc.render(ref, SPP)                 # race-free protocol
                 parity.update(frame_parity(full.cpu().numpy(), ref.buffers.accum.cpu().numpy()))
                 parity["against"] = "reference volume_rt_kernel (oracle/_ref), same parameter block, its own octree, same frame as timed"
-                if args.fast: parity["note"] = "fast mode is validated statistically (tests/test_bricks_gpu.py); flipped_frac is reported, not gated"
-                else: parity_fail |= parity["flipped_frac"] > MAX_FLIPPED
+                parity_fail |= parity["flipped_frac"] > MAX_FLIPPED
             else:
                 parity["against"] = "unavailable (oracle/_ref not in this snapshot, or > 600 instances: beyond the reference's capacity)"
         if world > 1: dist.barrier()
@@ -428,7 +433,7 @@ def main():
             if os.path.exists(tpath):
                 tj = json.load(open(tpath))
                 ent = tj if args.config == tj.get("baseline_config", 2) else tj.get("configs", {}).get(str(args.config))
-                if ent and not args.fast and world == 1 and ent.get("passes_per_launch") == (opts.get("passes_per_chunk") or 32):
+                if ent and not args.fast and not args.cells and world == 1 and ent.get("passes_per_launch") == (opts.get("passes_per_chunk") or 32):
                     traffic = ent["k_trace_dram_bytes_per_launch"]
                 break
         bytes_per_sample = 88.0 + 32.0 * lookups_per_sample          # framebuffer stream + 32 B per density lookup

@@ -166,6 +166,18 @@ int  vpt_debug_sampler_compare(vpt_tex_t tex, vpt_devptr_t d_pool, int dim_x, in
 int  vpt_bricks_destroy(vpt_devptr_t d_pool);
 int  vpt_set_brick_volume(vpt_context* ctx, vpt_devptr_t d_pool, int dim_x, int dim_y, int dim_z);
 
+/* ---- cell mode: one DRAM sector per look-up for grids no cache can hold -------------------------------------------
+ * vpt_cells_create re-lays a dense device grid as a CELL TABLE: for every texel cell (i, j, k) the eight corner texels a
+ * trilinear look-up in that cell blends (clamped at the upper faces), 32 contiguous, 32-byte aligned bytes, x fastest.  Eight
+ * times the memory of the grid (1024^3: 32 GiB -- sized for 180 GB of HBM), and ONE sector per look-up where the 2x2x2
+ * footprint costs four or five in the tiled array of the texture path.  vpt_set_cell_volume makes the trace kernel read volume
+ * 0 from it (lean instantiation, 2 rays per lane, the texture unit's arithmetic in software as in brick mode: same per-pixel
+ * tolerance, tests/test_bricks_gpu.py); same scene restrictions as brick mode; d_cells = 0 returns to the texture path. */
+int  vpt_cells_create(const float* d_dense, int dim_x, int dim_y, int dim_z, vpt_devptr_t* d_cells_out, unsigned long long* bytes_out);
+int  vpt_cells_read(vpt_devptr_t d_cells, unsigned long long first_cell, unsigned long long n_cells, float* h_out);       /* 8 floats per cell */
+int  vpt_cells_destroy(vpt_devptr_t d_cells);
+int  vpt_set_cell_volume(vpt_context* ctx, vpt_devptr_t d_cells, int dim_x, int dim_y, int dim_z);
+
 /* Equirectangular environment map float4 (main.cpp:945-978: wrap / clamp, linear, normalised). */
 int  vpt_texture_create_env(const float* host_rgba, unsigned width, unsigned height, vpt_tex_t* tex_out, void** array_out);
 /* The four sky-sampling tables the volumetric path integrator reads when environment_type == 0 (reference create_cdf,

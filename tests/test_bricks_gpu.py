@@ -74,6 +74,39 @@ def test_brick_pool_layout(perlin):
         assert got[125] == want.max() and got[126] == want.min() and got[127] == 0.0
 
 
+def test_cell_table_holds_the_eight_corners_of_every_cell(perlin):
+    dx, dy, dz = perlin.dims
+    perlin.build_cells()
+    assert perlin.cell_bytes == dx * dy * dz * 32
+    dense = perlin.dense.cpu().numpy().reshape(dz, dy, dx)
+    rng = np.random.RandomState(3)
+    cells = [(0, 0, 0), (dx - 1, dy - 1, dz - 1), (dx - 1, 0, dz - 1), (5, dy - 1, 7)] + [tuple(int(rng.randint(0, d)) for d in (dx, dy, dz)) for _ in range(40)]
+    for (i, j, k) in cells:
+        got = np.empty(8, dtype=np.float32)
+        V._native.check(V.lib.vpt_cells_read(perlin.cell_table, (k * dy + j) * dx + i, 1, got.ctypes.data_as(C.POINTER(C.c_float))), None, "vpt_cells_read")
+        i1, j1, k1 = min(i + 1, dx - 1), min(j + 1, dy - 1), min(k + 1, dz - 1)      # clamp addressing at the upper faces
+        want = [dense[kk, jj, ii] for kk in (k, k1) for jj in (j, j1) for ii in (i, i1)]   # corner = z << 2 | y << 1 | x
+        assert np.array_equal(got, np.array(want, dtype=np.float32)), (i, j, k)
+
+
+def test_cell_mode_meets_the_texture_path_tolerance(perlin):
+    """One sector per look-up instead of the texture unit: same seeds, same control flow, same per-pixel tolerance."""
+    scene = scene_of(perlin)
+    kw = dict(ray_depth=3, volume_depth=2)
+    par = V.Renderer(scene, 640, 400, kp=make_kp(**kw)); cel = V.Renderer(scene, 640, 400, kp=make_kp(**kw), cam=par.cam, options={"count_stats": 1})
+    cel.set_cell_volume(perlin)
+    scene.reset_blue_noise(); par.render(2)
+    scene.reset_blue_noise(); cel.render(2); torch.cuda.synchronize()
+    a = par.buffers.accum.cpu().numpy(); b = cel.buffers.accum.cpu().numpy()
+    frac = flipped_fraction(b, a)
+    print(f"cell mode vs texture path, 2 passes: flipped {frac:.4g}, max |d| {np.abs(a - b).max():.3g}; {cel.counters()['lookups']} look-ups")
+    assert float(a.mean()) > 1e-3 and np.isfinite(b).all() and frac <= MAX_FLIPPED
+    assert flipped_fraction(cel.buffers.depth.cpu().numpy()[:, None], par.buffers.depth.cpu().numpy()[:, None]) <= MAX_FLIPPED
+    cel.set_cell_volume(None)                                   # back to the texture path: bit-identical again
+    scene.reset_blue_noise(); cel.kp.iteration = 0; cel.render(2); torch.cuda.synchronize()
+    assert torch.equal(cel.buffers.accum, par.buffers.accum)
+
+
 def test_software_filter_against_texture_unit(perlin):
     """The brick sampler's blend against tex3D on a million random points: the production rule (the texture unit's hierarchical 8-bit
     corner weights, fitted on the device: tools/tex_weight_fit.py) must be bit-identical on nearly every fetch and within an ulp on the
@@ -163,10 +196,10 @@ def test_fast_mode_refuses_what_it_does_not_implement(perlin):
     scene = scene_of(perlin)
     r = V.Renderer(scene, 64, 64, kp=make_kp(ray_depth=1, integrator=1))
     r.set_brick_volume(perlin)
-    with pytest.raises(V.VptError, match="fast"):
+    with pytest.raises(V.VptError, match="brick / cell mode"):
         r.render_pass()
     two = V.Scene([perlin.instance(), perlin.instance(pos=(200, 0, 0))], env=synthetic_env(512, 256), keep=[perlin])
     r2 = V.Renderer(two, 64, 64, kp=make_kp(ray_depth=1)); r2.set_brick_volume(perlin)
-    with pytest.raises(V.VptError, match="fast"):
+    with pytest.raises(V.VptError, match="brick / cell mode"):
         r2.render_pass()
     r2.set_brick_volume(None); r2.render_pass(); torch.cuda.synchronize()       # parity mode still works on that scene

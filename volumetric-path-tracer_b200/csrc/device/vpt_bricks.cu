@@ -2,6 +2,8 @@
 //   k_fill_perlin   procedural density grid, restating the reference's fill_volume_buffer (source/texture_kernels.cu:76-128,
 //                   noise type 0 = cudaNoise::perlinNoise, thirdparty/cuda-noise/include/cuda_noise.cuh:574-619) with ZERO
 //                   jitter (the reference draws its sub-voxel jitter from an uninitialised curand state: quirk Q14, undefined)
+//   k_build_cells   dense x-fastest grid -> cell table: per texel cell (i, j, k) the eight corner texels it blends, 32 contiguous, 32-byte
+//                   aligned bytes: a trilinear look-up touches ONE DRAM sector (the tiled cudaArray of the texture path: 4-5).  8x the memory.
 //   k_build_bricks  dense x-fastest grid -> pool of 4x4x4-cell bricks, each stored with its +1 apron as 5x5x5 texels
 //                   (125 floats) + [125] brick max, [126] brick min, [127] 0  = 128 floats = 512 bytes, 512-byte aligned:
 //                   one contiguous cp.async.bulk (TMA, SASS UBLKCP) brings everything a trilinear look-up inside the brick
@@ -92,6 +94,26 @@ __global__ void k_build_bricks(const float* __restrict__ dense, int3 dims, int3 
     }
     for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
     if (lane == 0) { out[125] = mx; out[126] = mn; out[127] = 0.0f; }
+}
+
+// one thread per texel cell: its eight corner texels (clamp addressing at the upper faces), corner = z << 2 | y << 1 | x, as two float4
+__global__ void k_build_cells(const float* __restrict__ dense, int3 dims, float4* __restrict__ cells)
+{
+    const size_t n = (size_t)dims.x * dims.y * dims.z;
+    for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(c % dims.x), y = (int)((c / dims.x) % dims.y), z = (int)(c / ((size_t)dims.x * dims.y));
+        const int x1 = min(x + 1, dims.x - 1), y1 = min(y + 1, dims.y - 1), z1 = min(z + 1, dims.z - 1);
+        const size_t r00 = ((size_t)z * dims.y + y) * dims.x, r01 = ((size_t)z * dims.y + y1) * dims.x;
+        const size_t r10 = ((size_t)z1 * dims.y + y) * dims.x, r11 = ((size_t)z1 * dims.y + y1) * dims.x;
+        cells[2 * c + 0] = make_float4(dense[r00 + x], dense[r00 + x1], dense[r01 + x], dense[r01 + x1]);
+        cells[2 * c + 1] = make_float4(dense[r10 + x], dense[r10 + x1], dense[r11 + x], dense[r11 + x1]);
+    }
+}
+
+cudaError_t launch_build_cells(const float* d_dense, int dx, int dy, int dz, float4* d_cells, cudaStream_t s)
+{
+    k_build_cells<<<148 * 32, 256, 0, s>>>(d_dense, make_int3(dx, dy, dz), d_cells);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fill_perlin(float* d_buffer, int dx, int dy, int dz, float scale, int seed, cudaStream_t s)

@@ -132,6 +132,7 @@ VPT_DEV float3 mat3_mul(const float m[9], float3 v) {
     return f3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
 }
 
+#include "vpt_texfilter.cuh"
 #include "vpt_trace.cuh"
 #ifndef VPT_LEVEL_A_MODULE          // the level (A) cubin exports exactly one entry: no wavefront kernels in it
 #include "vpt_trace_brick.cuh"

@@ -483,6 +483,10 @@ static cudaError_t launch_trace_t(const FrameArgs& fa, const vpt_atmosphere* atm
 cudaError_t launch_trace(const FrameArgs& fa, const vpt_atmosphere* atm, bool lean, int slots, int n_ctas, cudaStream_t s)
 {
     if (atm) return launch_trace_t<1, false, 3>(fa, atm, n_ctas, s);
+    if (fa.cell_table) {                                                        // the host only sets it for lean scenes
+        k_trace<0, true, 2, true><<<n_ctas, kTraceThreads, trace_smem_bytes(2), s>>>(fa, NoAtmo{});
+        return cudaGetLastError();
+    }
     if (slots == 2) return lean ? launch_trace_t<0, true, 2>(fa, nullptr, n_ctas, s) : launch_trace_t<0, false, 2>(fa, nullptr, n_ctas, s);
     return lean ? launch_trace_t<0, true, 3>(fa, nullptr, n_ctas, s) : launch_trace_t<0, false, 3>(fa, nullptr, n_ctas, s);
 }
@@ -499,8 +503,13 @@ static cudaError_t trace_init_t(int* max_ctas)
 
 static size_t brick_smem_bytes() { return (size_t)kBrickThreads * kBrickBytes; }
 
-cudaError_t trace_kernels_init(int max_ctas[6])
+cudaError_t trace_kernels_init(int max_ctas[7])
 {
+    {
+        cudaError_t e0 = cudaFuncSetAttribute(k_trace<0, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem_bytes(2));
+        if (e0 == cudaSuccess) e0 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas[6], k_trace<0, true, 2, true>, kTraceThreads, trace_smem_bytes(2));
+        if (e0 != cudaSuccess) return e0;
+    }
     cudaError_t e = trace_init_t<0, false, 3>(&max_ctas[0]);
     if (e == cudaSuccess) e = trace_init_t<0, true, 3>(&max_ctas[1]);
     if (e == cudaSuccess) e = trace_init_t<1, false, 3>(&max_ctas[2]);

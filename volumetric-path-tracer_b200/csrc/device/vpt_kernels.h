@@ -47,6 +47,9 @@ struct FrameArgs {
     float4 *planeA, *planeB, *planeC, *planeD;   // planeD (env_pos) only for environment_type == 0, else null
     // optional statistics: [0] volume lookups, [1] lane-steps, [2] warp step iterations, [3] lane transitions, [4] warp transition rounds
     unsigned long long* counters;
+    // cell table of volume 0 (vpt_cells_create; null = texture path): per texel cell its eight corner values, 32 bytes = ONE sector per look-up
+    const float4* cell_table;
+    int       cell_nx, cell_ny, cell_nz;
 };
 
 cudaError_t launch_prepare_scene(const vpt_gpu_vdb* vols, const vpt_octnode* root, SceneTables* out, OctInternal* internal,
@@ -54,14 +57,15 @@ cudaError_t launch_prepare_scene(const vpt_gpu_vdb* vols, const vpt_octnode* roo
 cudaError_t launch_prepare_volumes(const vpt_gpu_vdb* vols, const SceneTables& hdr, SceneTables* out, VolumeRec* vrec, cudaStream_t s);
 cudaError_t launch_generate(const FrameArgs& fa, int n_passes, cudaStream_t s);
 // atm != null selects the volumetric path integrator variant of the trace kernel
-cudaError_t launch_trace(const FrameArgs& fa, const vpt_atmosphere* atm, bool lean, int slots, int n_ctas, cudaStream_t s);   // slots: rays per lane, 2 or 3
+cudaError_t launch_trace(const FrameArgs& fa, const vpt_atmosphere* atm, bool lean, int slots, int n_ctas, cudaStream_t s);   // slots: rays per lane, 2 or 3; fa.cell_table != null: the lean 2-slot cell-table instantiation
 // per device: dynamic shared memory opt-in of the trace kernels + CTAs per SM of [generic, lean, volumetric path, brick]
-cudaError_t trace_kernels_init(int max_ctas[6]);      // [0..2] generic / lean / volumetric path at 3 rays per lane, [3] k_trace_brick, [4..5] generic / lean at 2 rays per lane
+cudaError_t trace_kernels_init(int max_ctas[7]);      // [6]: lean, 2 rays per lane, cell table      // [0..2] generic / lean / volumetric path at 3 rays per lane, [3] k_trace_brick, [4..5] generic / lean at 2 rays per lane
 // fast mode: lean direct integrator reading the density from a brick pool (vpt_trace_brick.cuh); dims = voxels per axis
 cudaError_t launch_trace_brick(const FrameArgs& fa, const float* pool, const int dims[3], int n_ctas, cudaStream_t s);
 cudaError_t launch_sampler_compare(unsigned long long tex, const float* pool, const int dims[3], int n, unsigned seed, double* d_out12, cudaStream_t s);
 cudaError_t launch_fill_perlin(float* d_buffer, int dx, int dy, int dz, float scale, int seed, cudaStream_t s);
 cudaError_t launch_build_bricks(const float* d_dense, int dx, int dy, int dz, float* d_bricks, cudaStream_t s);
+cudaError_t launch_build_cells(const float* d_dense, int dx, int dy, int dz, float4* d_cells, cudaStream_t s);
 // sky != null selects the environment_type == 0 variant (host copy of the caller's AtmosphereParameters)
 // Peer-memory exchange (multi-GPU, csrc/host/vpt_comm.cpp): the call's LAST resolve kernel stores every finished pixel straight into the
 // full-frame buffer of every rank (its own included) at the pixel's global position, over NVLink peer mappings -- the all-gather and

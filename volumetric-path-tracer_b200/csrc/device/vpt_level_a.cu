@@ -120,7 +120,7 @@ volume_rt_kernel(const vpt_camera cam, const vpt_light_list lights, const vpt_gp
         fa.bn_table = nullptr; fa.n_passes = 1; fa.passes_per_block = 1; fa.debug_flags = 0; fa.sched_min_lanes = 20; fa.queue_count = nullptr; fa.queue_head = nullptr;
         fa.planeA = fa.planeB = fa.planeC = nullptr;
         fa.planeD = reinterpret_cast<float4*>(kp.raw_buffer);          // env_pos scratch of the sphere branch: this pixel's raw_buffer entry, rewritten at the end
-        fa.counters = nullptr;
+        fa.counters = nullptr; fa.cell_table = nullptr; fa.cell_nx = fa.cell_ny = fa.cell_nz = 0;
         sh.fs.vol0 = make_volume_rec(gpu_vdb[0]);
         sh.sph = load_sphere(&sphere);
         sh.tc.inv_max = 1.0f / sc.max_extinction;

@@ -152,10 +152,24 @@ VPT_DEV void store_walk(const PV& pv, int s, const PathState& st)
     pv.u(30, s) = (st.packed & ~kExitMask) | ((uint32_t)st.exit_reason << 6);
 }
 
+// Density of volume 0 from its cell table (vpt_cells_create): the eight corner texels of the cell under the point are 32 contiguous,
+// aligned bytes -- one DRAM sector per look-up instead of the four or five a 2x2x2 footprint costs in the tiled texture array --
+// blended with the texture unit's own arithmetic (vpt_texfilter.cuh).  Measured on the 1024^3 grid: DRAM traffic falls to the algorithmic
+// 32 B per look-up, the time does not change: an experiment kept for that evidence, not a faster path.
+VPT_DEV float cell_density(const FrameArgs& fa, const VolumeRec& v, float3 p)
+{
+    float3 uvw;
+    if (!volume_coord(v, p, uvw)) return .0f;
+    const TexCell q = tex_cell<0>(uvw, fa.cell_nx, fa.cell_ny, fa.cell_nz);
+    const float4* c = fa.cell_table + 2 * (((size_t)q.k * (size_t)fa.cell_ny + (size_t)q.j) * (size_t)fa.cell_nx + (size_t)q.i);
+    const float4 lo = __ldg(c), hi = __ldg(c + 1);
+    return tex_blend<0>(q, lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w);
+}
+
 // ---- OP_STEP -------------------------------------------------------------------------------------------------
 // kLean: single volume, no emission walk, no point lights -- the headline configuration; those features' code is compiled out
 // of that instantiation (smaller hot loop: the kernel is fetch-stall bound)
-template <bool kLean>
+template <bool kLean, bool kCells = false>
 VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph, uint32_t& nlook,
                        float* beta = nullptr, int beta_stride = 0)   // kLean: the path's throughput in the parked record (x, y, z one stride apart)
 {
@@ -188,7 +202,7 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
         st.aux += leaf_emission(sc, fs.vol0, leaf, st.wpos, reinterpret_cast<const float3*>(kp.emission_texture), kp.emission_pivot, kp.emission_scale);
         return;
     }
-    const float density = kLean ? 0.0f + volume_density(fs.vol0, st.wpos) : leaf_density(sc, fs.vol0, leaf, st.wpos);
+    const float density = kLean ? 0.0f + (kCells ? cell_density(fa, fs.vol0, st.wpos) : volume_density(fs.vol0, st.wpos)) : leaf_density(sc, fs.vol0, leaf, st.wpos);
     if (st.mode == W_DELTA) {
         if (st.alpha < 1.0f) st.alpha += density;
         if (pmul(tc.inv_max, density) > st.rng.next()) {
@@ -434,7 +448,7 @@ VPT_DEV void write_sample(const PathState& st, const FrameArgs& fa)
 // caller's AtmosphereParameters in the kernel (sky radiance decides whether a transmittance walk is run at all)
 struct NoAtmo { int pad[4]; };
 
-template <int kInteg, bool kLean, int kSlots>
+template <int kInteg, bool kLean, int kSlots, bool kCells = false>
 __global__ void __launch_bounds__(kTraceThreads, trace_min_ctas(kSlots))
 k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atmosphere, NoAtmo>::type atm)
 {
@@ -556,7 +570,7 @@ k_trace(const FrameArgs fa, const typename std::conditional<kInteg != 0, vpt_atm
                     break;
                 }
                 if (cur >= 0) {
-                    walk_step<kLean>(st, fs, fa, tc, sph, nlook, &pv.f(9, cur), kPool); lane_steps++;
+                    walk_step<kLean, kCells>(st, fs, fa, tc, sph, nlook, &pv.f(9, cur), kPool); lane_steps++;
                     if (st.op != OP_STEP) {                        // walk ended: park the ray with its new tag
                         store_walk(pv, cur, st);
                         if (cur == 0) tag0 = st.op; else if (cur == 1) tag1 = st.op; else tag2 = st.op;

@@ -119,6 +119,7 @@ int vpt_set_option(vpt_context* c, const char* key, int value) {
     if (k == "passes_per_chunk") { if (value < 0 || value > 64) return fail(c, VPT_ERR_INVALID, "passes_per_chunk must be 0 (automatic) or 1..64"); c->chunk_auto = value == 0; if (value) c->passes_per_chunk = value; }
     else if (k == "max_scratch_mb") { if (value < 64) return fail(c, VPT_ERR_INVALID, "max_scratch_mb must be >= 64"); c->max_scratch_bytes = (size_t)value << 20; }
     else if (k == "gather_async") { c->gather_async = value ? 1 : 0; }
+    else if (k == "l2_sector_fetch") { c->l2_sector_fetch = value ? 1 : 0; }
     else if (k == "trace_slots") { if (value != 0 && value != 2 && value != 3) return fail(c, VPT_ERR_INVALID, "trace_slots must be 0 (by grid size), 2 or 3"); c->trace_slots = value; }
     else if (k == "ctas_per_sm") { if (value < 0 || value > 8) return fail(c, VPT_ERR_INVALID, "ctas_per_sm must be 0..8"); c->ctas_per_sm = value; }
     else if (k == "sched_min_lanes") { if (value < 1 || value > 32) return fail(c, VPT_ERR_INVALID, "sched_min_lanes must be 1..32"); c->sched_min_lanes = value; }
@@ -267,12 +268,13 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
             c->cached_volumes = d_volumes; c->cached_root = d_root; c->cached_generation = registered ? ent.generation : 0ull;
         }
     }
-    if (c->brick_pool) {
-        // fast mode reads volume 0 from the brick pool: only the lean case of the direct integrator is built for it
+    if (c->brick_pool || c->cell_table) {
+        // brick / cell mode read volume 0 from their own copy of the grid: only the lean case of the direct integrator is built for them
         vpt::SceneEntry ent;
         const bool ok = vpt::scene_registry_find(d_root, &ent) && ent.n == 1 && !(ent.any_flags & 1u) && !(kp.emission_scale > 0.0f) &&
-                        fa.lights.num_lights == 0 && kp.integrator == 0;
-        if (!ok) return fail(c, VPT_ERR_UNSUPPORTED, "brick (fast) mode needs a vpt_octree_build scene of ONE volume without colour grid, the direct integrator, no emission and no point lights");
+                        fa.lights.num_lights == 0 && kp.integrator == 0 && !c->force_generic;
+        if (!ok) return fail(c, VPT_ERR_UNSUPPORTED, "brick / cell mode needs a vpt_octree_build scene of ONE volume without colour grid, the direct integrator, no emission and no point lights");
+        if (c->brick_pool && c->cell_table) return fail(c, VPT_ERR_INVALID, "brick mode and cell mode are both set");
     }
     // "lean" = nothing but one volume, sun and environment in play (the headline configuration)
     const bool lean = c->scene_single_volume && !(kp.emission_scale > 0.0f) && fa.lights.num_lights == 0 && kp.integrator == 0 && !c->force_generic;
@@ -319,18 +321,20 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
     // rays per warp.  Measured: 1024^3 grid 158 -> 104 ms, 512^3 92 -> 77 ms, 1000 instances 94 -> 82 ms; the
     // L2-resident scenes lose with it (dragon 7.1 -> 8.2 ms, fireball 185 -> 282 ms).
     int slots = 3;
-    if (!vol_integ && !c->brick_pool) {
+    if (c->cell_table) slots = 2;
+    else if (!vol_integ && !c->brick_pool) {
         if (c->trace_slots) slots = c->trace_slots;
         else {
             vpt::SceneEntry ent;
             if (vpt::scene_registry_find(d_root, &ent) && (ent.max_grid_bytes > 2ull * c->l2_bytes || ent.n >= 64)) slots = 2;
         }
     }
-    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : c->max_ctas[c->brick_pool ? 3 : vol_integ ? 2 : (slots == 2 ? (lean ? 5 : 4) : (lean ? 1 : 0))];
+    int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : c->max_ctas[c->brick_pool ? 3 : c->cell_table ? 6 : vol_integ ? 2 : (slots == 2 ? (lean ? 5 : 4) : (lean ? 1 : 0))];
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int trace_ctas = c->num_sms * ctas_per_sm;
 
     fa.counters = c->count_stats ? c->d_stats : nullptr;
+    fa.cell_table = c->cell_table; fa.cell_nx = c->cell_dims[0]; fa.cell_ny = c->cell_dims[1]; fa.cell_nz = c->cell_dims[2];
     auto timed = [&](int kind, auto&& fn) -> cudaError_t {
         if (!c->profile) return fn();
         vpt_context::Ev ev; ev.kind = kind;
@@ -500,6 +504,43 @@ int vpt_debug_sampler_compare(vpt_tex_t tex, vpt_devptr_t d_pool, int dx, int dy
     cudaFree(d_out);
     if (e != cudaSuccess) return fail(nullptr, VPT_ERR_CUDA, std::string("vpt_debug_sampler_compare: ") + cudaGetErrorString(e));
     for (int m = 0; m < 3; ++m) out12[m * 4 + 3] = (double)n_points;
+    return VPT_OK;
+}
+
+int vpt_cells_create(const float* d_dense, int dx, int dy, int dz, vpt_devptr_t* d_cells_out, unsigned long long* bytes_out) {
+    if (!d_dense || !d_cells_out || dx < 1 || dy < 1 || dz < 1) return fail(nullptr, VPT_ERR_INVALID, "vpt_cells_create: bad arguments");
+    const size_t n = (size_t)dx * dy * dz;
+    float4* cells = nullptr;
+    cudaError_t e = cudaMalloc(&cells, n * 32);
+    if (e != cudaSuccess) return fail(nullptr, VPT_ERR_CUDA, std::string("vpt_cells_create: ") + std::to_string(n * 32 >> 20) + " MiB: " + cudaGetErrorString(e));
+    e = vpt::launch_build_cells(d_dense, dx, dy, dz, cells, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(cells); return fail(nullptr, VPT_ERR_CUDA, std::string("vpt_cells_create: ") + cudaGetErrorString(e)); }
+    *d_cells_out = (vpt_devptr_t)(uintptr_t)cells;
+    if (bytes_out) *bytes_out = (unsigned long long)n * 32ull;
+    return VPT_OK;
+}
+
+int vpt_cells_read(vpt_devptr_t d_cells, unsigned long long first_cell, unsigned long long n_cells, float* h_out) {
+    if (!d_cells || !h_out) return fail(nullptr, VPT_ERR_INVALID, "vpt_cells_read: null argument");
+    VPT_CUDA(nullptr, cudaMemcpy(h_out, reinterpret_cast<const char*>((uintptr_t)d_cells) + first_cell * 32ull, n_cells * 32ull, cudaMemcpyDeviceToHost));
+    return VPT_OK;
+}
+
+int vpt_cells_destroy(vpt_devptr_t d_cells) { if (d_cells) cudaFree((void*)(uintptr_t)d_cells); return VPT_OK; }
+
+int vpt_set_cell_volume(vpt_context* c, vpt_devptr_t d_cells, int dx, int dy, int dz) {
+    if (!c) return VPT_ERR_INVALID;
+    if (d_cells && (dx < 1 || dy < 1 || dz < 1)) return fail(c, VPT_ERR_INVALID, "vpt_set_cell_volume: bad dimensions");
+    c->cell_table = reinterpret_cast<const float4*>((uintptr_t)d_cells);
+    c->cell_dims[0] = dx; c->cell_dims[1] = dy; c->cell_dims[2] = dz;
+    // a cell is one 32-byte sector: option "l2_sector_fetch" asks the L2 not to widen a miss to a larger DRAM fetch while this mode is on
+    // (cudaLimitMaxL2FetchGranularity, a DEVICE-wide hint: the streaming kernels lose ~4 % with it, so it is not the default)
+    if (d_cells && c->l2_sector_fetch) {
+        if (!c->l2_fetch_default) cudaDeviceGetLimit(&c->l2_fetch_default, cudaLimitMaxL2FetchGranularity);
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    } else if (c->l2_fetch_default) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, c->l2_fetch_default);
+    cudaGetLastError();
     return VPT_OK;
 }
 

@@ -24,7 +24,9 @@ struct vpt_context {
     bool   scene_single_volume = false;
     size_t cap_vrec = 0;              // VolumeRec capacity (grows with the instance count)
     int*   h_pinned = nullptr;        // one pinned word for the 4-byte read-back a foreign octree needs
-    int    max_ctas[6] = {0, 0, 0, 0, 0, 0};   // trace kernel occupancy: [0] generic, [1] lean, [2] volumetric path, [3] brick (fast mode), [4] generic / [5] lean at 2 rays per lane
+    int    max_ctas[7] = {0, 0, 0, 0, 0, 0, 0};   // trace kernel occupancy: [0] generic, [1] lean, [2] volumetric path, [3] brick mode, [4] generic / [5] lean at 2 rays per lane, [6] lean + cell table
+    size_t l2_fetch_default = 0; int l2_sector_fetch = 0;     // option "l2_sector_fetch" (cell mode)
+    const float4* cell_table = nullptr; int cell_dims[3] = {0, 0, 0};   // vpt_set_cell_volume
     int    trace_slots = 0;              // option "trace_slots": rays per lane of k_trace, 0 = by grid size (2 when the grid is larger than twice the L2)
     size_t l2_bytes = 0;
     const float* brick_pool = nullptr; int brick_dims[3] = {0, 0, 0};   // fast mode: density of volume 0 as a brick pool (vpt_set_brick_volume)

@@ -109,6 +109,14 @@ class Renderer:
             if not getattr(volume, "brick_pool", 0): volume.build_bricks()
             check(lib.vpt_set_brick_volume(self.ctx, volume.brick_pool, *volume.dims), self.ctx, "vpt_set_brick_volume")
 
+    def set_cell_volume(self, volume):
+        """Cell mode: trace volume 0 from `volume`'s cell table (None: back to the texture path)."""
+        if volume is None:
+            check(lib.vpt_set_cell_volume(self.ctx, 0, 0, 0, 0), self.ctx, "vpt_set_cell_volume")
+        else:
+            if not getattr(volume, "cell_table", 0): volume.build_cells()
+            check(lib.vpt_set_cell_volume(self.ctx, volume.cell_table, *volume.dims), self.ctx, "vpt_set_cell_volume")
+
     def counters(self, reset=True):
         out = (C.c_ulonglong * 8)()
         check(lib.vpt_get_counters(self.ctx, out, 1 if reset else 0), self.ctx, "vpt_get_counters")

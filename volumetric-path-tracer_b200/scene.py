@@ -261,6 +261,15 @@ class Volume:
         self.brick_pool = pool.value; self.brick_bytes = int(nbytes.value)
         return self.brick_pool
 
+    def build_cells(self):
+        """Cell table of the density grid for cell mode (vpt_cells_create: 32 bytes per texel cell, one sector per look-up)."""
+        assert getattr(self, "dense", None) is not None, "no dense device grid kept for this volume"
+        tab = C.c_uint64(0); nbytes = C.c_ulonglong(0)
+        dx, dy, dz = self.dims
+        check(lib.vpt_cells_create(C.c_void_p(self.dense.data_ptr()), dx, dy, dz, C.byref(tab), C.byref(nbytes)), None, "vpt_cells_create")
+        self.cell_table = tab.value; self.cell_bytes = int(nbytes.value)
+        return self.cell_table
+
     @staticmethod
     def load_vdb(path, density="density", emission="heat", color="Cd"):
         got = load_vdb_grid(path, density)
