@@ -108,14 +108,18 @@ k_generate(const FrameArgs fa)
     const FrameGeom& g = fa.geom;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = blockIdx.x * 32 + warp * 8 + (lane & 7);
-    const int lr = blockIdx.y * 4 + (lane >> 3);
+    const SphereRec sph = load_sphere(fa.sphere);
+    // one block = a run of 32x4 pixel tiles x a run of passes: enough (tile, pass) pairs per block to amortise the octree / table staging
+    // above -- many passes of one tile when passes are fused, several tiles when the caller renders pass by pass; a small local frame
+    // (multi-GPU shard, low resolution) splits the chunk's passes over blockIdx.z instead: see launch_generate
+    const int tiles_x = (g.width + 31) / 32, n_tiles = tiles_x * ((g.local_rows + 3) / 4);
+    for (int tile = blockIdx.x * fa.tiles_per_block; tile < min(n_tiles, (int)(blockIdx.x + 1) * fa.tiles_per_block); ++tile) {
+    const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
+    const int x = tile_x * 32 + warp * 8 + (lane & 7);
+    const int lr = tile_y * 4 + (lane >> 3);
     const int y = global_row(g, lr);
     const bool valid = (x < g.width) && (lr < g.local_rows) && (y < g.height);
 
-    const SphereRec sph = load_sphere(fa.sphere);
-    // one block = one 32x4 pixel tile, all passes of the chunk (amortises the octree / table staging above)
-    // a small local frame (multi-GPU shard, low resolution) splits the chunk's passes over blockIdx.z: see launch_generate
     const int pass_begin = blockIdx.z * fa.passes_per_block;
     const int pass_end = min(fa.n_passes, pass_begin + fa.passes_per_block);
     // blue-noise jitter of each pass, from the per-chunk table written by k_bn_prepare; the value of the NEXT pass is requested one
@@ -232,6 +236,7 @@ k_generate(const FrameArgs fa)
         }
     }
     }   // pass loop
+    }   // tile loop
 }
 
 
@@ -455,15 +460,17 @@ cudaError_t launch_prepare_volumes(const vpt_gpu_vdb* vols, const SceneTables& h
 
 cudaError_t launch_generate(const FrameArgs& fa, int n_passes, cudaStream_t s)
 {
-    dim3 grid((fa.geom.width + 31) / 32, (fa.geom.local_rows + 3) / 4, 1);
     FrameArgs a = fa; a.n_passes = n_passes;
-    // one block = one 32x4 pixel tile x a run of passes.  Keep >= ~8 waves of blocks (148 SMs x 7 resident blocks) so the tail of the
-    // grid does not idle the SMs when the local frame is small; never fewer than 4 passes per block (amortises the table staging).
+    // one block = a run of 32x4 pixel tiles x a run of passes.  Keep >= ~8 waves of blocks (148 SMs x 7 resident blocks) so the tail of the
+    // grid does not idle the SMs when the local frame is small; never fewer than 4 (tile, pass) pairs per block (amortises the table
+    // staging: one pass per call used to spend half of this kernel on it).
     int ppb = n_passes;
-    const long long tiles = (long long)grid.x * grid.y;
+    const long long tiles = (long long)((fa.geom.width + 31) / 32) * ((fa.geom.local_rows + 3) / 4);
     while (ppb > 4 && tiles * ((n_passes + ppb - 1) / ppb) < 8288) ppb = (ppb + 1) / 2;
-    a.passes_per_block = ppb;
-    grid.z = (unsigned)((n_passes + ppb - 1) / ppb);
+    int tpb = 1;
+    while (ppb * tpb < 4 && tiles / (tpb * 2) >= 2368) tpb *= 2;
+    a.passes_per_block = ppb; a.tiles_per_block = tpb;
+    dim3 grid((unsigned)((tiles + tpb - 1) / tpb), 1, (unsigned)((n_passes + ppb - 1) / ppb));
     k_generate<<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
 }

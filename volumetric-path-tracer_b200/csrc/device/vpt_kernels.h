@@ -39,6 +39,7 @@ struct FrameArgs {
     const float2* bn_table;        // [pass][65536] blue-noise jitter of the chunk
     int       n_passes;            // passes in this chunk (k_generate loops over them)
     int       passes_per_block;    // k_generate: passes handled by one block (blockIdx.z selects the run)
+    int       tiles_per_block;     // k_generate: consecutive 32x4 tiles handled by one block (blockIdx.x selects the run)
     int       debug_flags;         // development switches (0 in production)
     int       sched_min_lanes;     // trace scheduler: lanes an operation must gather before it pre-empts stepping
     unsigned* queue_count;
