@@ -90,7 +90,7 @@ VPT_DEV float3 ld3(const vpt_f3& v) { return f3(v.x, v.y, v.z); }
 
 // global row of a local row under the interleaved-stripe partition (identity for one rank)
 VPT_DEV int global_row(const FrameGeom& g, int lr) {
-    const int s = g.stripe_shift >= 0 ? (lr >> g.stripe_shift) : lr / g.stripe_h;
+    const int s = (g.stripe_h & (g.stripe_h - 1)) == 0 ? (lr >> (__ffs(g.stripe_h) - 1)) : lr / g.stripe_h;   // power-of-two stripes: no division
     return (s * g.n_ranks + g.rank) * g.stripe_h + (lr - s * g.stripe_h);
 }
 

@@ -20,7 +20,6 @@ struct FrameGeom {
     int local_rows;         // rows stored locally (padded so every rank holds the same count)
     int n_local;            // local_rows * width
     int stripe_h, n_ranks, rank;
-    int stripe_shift;       // log2(stripe_h) when it is a power of two (index arithmetic without a division), else -1
 };
 
 // Everything a per-frame kernel needs, passed by value (about 600 B of kernel parameter space).
@@ -39,7 +38,6 @@ struct FrameArgs {
     const float2* bn_table;        // [pass][65536] blue-noise jitter of the chunk
     int       n_passes;            // passes in this chunk (k_generate loops over them)
     int       passes_per_block;    // k_generate: passes handled by one block (blockIdx.z selects the run)
-    int       tiles_per_block;     // k_generate: consecutive 32x4 tiles handled by one block (blockIdx.x selects the run)
     int       debug_flags;         // development switches (0 in production)
     int       sched_min_lanes;     // trace scheduler: lanes an operation must gather before it pre-empts stepping
     unsigned* queue_count;
@@ -51,6 +49,7 @@ struct FrameArgs {
     // cell table of volume 0 (vpt_cells_create; null = texture path): per texel cell its eight corner values, 32 bytes = ONE sector per look-up
     const float4* cell_table;
     int       cell_nx, cell_ny, cell_nz;
+    int       tiles_per_block;     // k_generate: consecutive 32x4 tiles handled by one block (blockIdx.x selects the run)
 };
 
 cudaError_t launch_prepare_scene(const vpt_gpu_vdb* vols, const vpt_octnode* root, SceneTables* out, OctInternal* internal,

@@ -102,7 +102,9 @@ VPT_DEV void store_ray(const PV& pv, int s, const PathState& st)
 
 VPT_DEV void ray_rng_init(PathState& st, const FrameArgs& fa, uint32_t k)
 {
-    st.rng.init(ray_global_pixel(fa.geom, st.lp), fa.kp.iteration + st.pass, k);       // st.lp: the ray's pixel word (vpt_frame.cuh)
+    uint32_t idx = st.lp;                                    // the ray's pixel word (vpt_frame.cuh): the pixel index itself for one rank
+    if (fa.geom.n_ranks > 1) idx = ray_global_pixel(fa.geom, st.lp);
+    st.rng.init(idx, fa.kp.iteration + st.pass, k);
 }
 
 template <class PV>
@@ -431,7 +433,9 @@ VPT_DEV void advance(PathState& st, const FrameShared& fs, const FrameArgs& fa, 
 template <int kInteg>
 VPT_DEV void write_sample(const PathState& st, const FrameArgs& fa)
 {
-    const size_t o = (size_t)st.pass * fa.geom.n_local + ray_local_pixel(fa.geom, st.lp);
+    uint32_t lp = st.lp;
+    if (fa.geom.n_ranks > 1) lp = ray_local_pixel(fa.geom, st.lp);
+    const size_t o = (size_t)st.pass * fa.geom.n_local + lp;
     fa.planeA[o] = make_float4(st.dir.x, st.dir.y, st.dir.z, st.alpha);                 // final direction, tr
     fa.planeB[o] = make_float4(st.L.x, st.L.y, st.L.z, st.depth);                       // L, depth
     fa.planeC[o] = make_float4(st.beta.x, st.beta.y, st.beta.z, 1.f);                   // beta

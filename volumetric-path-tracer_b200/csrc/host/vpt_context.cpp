@@ -49,8 +49,6 @@ vpt::FrameGeom vpt::make_frame_geom(const vpt_context* c, unsigned w, unsigned h
         g.local_rows = per_rank * g.stripe_h;
     }
     g.n_local = g.local_rows * g.width;
-    g.stripe_shift = -1;
-    for (int sh = 0; sh < 16; ++sh) if ((1 << sh) == g.stripe_h) g.stripe_shift = sh;
     return g;
 }
 
