@@ -1,8 +1,7 @@
 #!/bin/bash
-# same-box A/B of the headline frame: commit c3fc45b, the current tree, and layout variants (kernel times)
+# same-box A/B of the headline frame over library variants (kernel times); VARIANTS="libA.so libB.so"
 cd "$(dirname "$0")/.."
-show='import sys,json; d=json.loads(sys.stdin.read()); r=d["roofline"]; print(round(d["value"],1), round(d["ms_per_step"],3), {k: round(v,3) for k,v in r["kernel_ms_per_step"].items()})'
-echo "== old"; (cd _old_ab && timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | tail -1 | python -c "$show")
+show='import sys,json; d=json.loads(sys.stdin.read()); r=d["roofline"]; print(round(d["value"],1), round(d["ms_per_step"],3), {k: round(v,3) for k,v in r["kernel_ms_per_step"].items()}, "simt", round(r["step_loop_simt_efficiency"],3))'
 for lib in libvpt_b200.so $VARIANTS; do
-echo "== $lib"; VPT_LIB_NAME=$lib timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | tail -1 | python -c "$show"
+echo "== $lib"; VPT_LIB_NAME=$lib timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline $EXTRA 2>/dev/null | tail -1 | python -c "$show"
 done

@@ -171,14 +171,21 @@ VPT_DEV float cell_density(const FrameArgs& fa, const VolumeRec& v, float3 p)
 // ---- OP_STEP -------------------------------------------------------------------------------------------------
 // kLean: single volume, no emission walk, no point lights -- the headline configuration; those features' code is compiled out
 // of that instantiation (smaller hot loop: the kernel is fetch-stall bound)
+// the per-step sphere test of a delta walk is rare (only lines that may hit the sphere): out of line, it keeps the hot loop shorter (6.88 -> 6.82 ms)
+__device__ __noinline__ bool sphere_intersect_cold(const SphereRec& s, float3 ray_pos, float3 ray_dir, float& t_min, float& t_max) { return sphere_intersect(s, ray_pos, ray_dir, t_min, t_max); }
 template <bool kLean, bool kCells = false>
 VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa, const TraceConsts& tc, const SphereRec& sph, uint32_t& nlook,
                        float* beta = nullptr, int beta_stride = 0)   // kLean: the path's throughput in the parked record (x, y, z one stride apart)
 {
     const SceneTables& sc = fs.sc;
     const vpt_kernel_params& kp = fa.kp;
+    // ONE point location per call: an empty node is hopped over (no draw consumed) and the call returns.  A second and a third in-line copy
+    // were measured: 7.17 ms and 8.04 ms of trace time on the headline frame against 6.88 ms -- the kernel is bound by instruction fetch,
+    // every copy of the octree descent in the hot loop costs more than the iterations it saves.
     int leaf = oct_locate_or_skip(fs.oct, sc, st.wpos, st.wdir);
-    if (leaf == -2) leaf = oct_locate_or_skip(fs.oct, sc, st.wpos, st.wdir);   // hop over up to two empty nodes per call (no draw consumed)
+#if defined(VPT_WALK_HOPS) && VPT_WALK_HOPS >= 2
+    if (leaf == -2) leaf = oct_locate_or_skip(fs.oct, sc, st.wpos, st.wdir);
+#endif
     if (leaf == -2) return;
     if (leaf == -1) { st.op = OP_GLUE; st.exit_reason = EX_OUTSIDE; return; }
 
@@ -186,7 +193,7 @@ VPT_DEV void walk_step(PathState& st, const FrameShared& fs, const FrameArgs& fa
         // distance to the box exit (or to the sphere) from the CURRENT position, every step (:1647-1651)
         float t_min, t_max, geo_dist = .0f;
         aabb_intersect(sc.root_pmin, sc.root_pmax, st.wpos, st.wdir, t_min, st.distance);
-        if (!st.sphere_free && sphere_intersect(sph, st.wpos, st.wdir, geo_dist, t_max)) st.distance = geo_dist;
+        if (!st.sphere_free && sphere_intersect_cold(sph, st.wpos, st.wdir, geo_dist, t_max)) st.distance = geo_dist;
     }
     const float u = st.rng.next();
     // t -= log(1-u) * a * b, as the reference build evaluates it: fma(b, a * (lg2(1-u) * -ln2), t)
