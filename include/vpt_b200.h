@@ -47,7 +47,7 @@ int  vpt_abi_sizes(size_t* out, int n);
 /* Tunables: "passes_per_chunk" (1..64 passes fused per generate/trace/resolve round; 0 = automatic, the default: 32, or 64 when the
  * local frame has at most 2^20 pixels), "max_scratch_mb" (cap of the per-round ray queue + sample planes, default 12288),
  * "gather_async" (see vpt_comm_*),
- * "sched_min_lanes" (1..32, lanes an operation must gather in a warp before it pre-empts stepping, default 20),
+ * "sched_min_lanes" (1..32, lanes an operation must gather in a warp before it pre-empts stepping, default 26),
  * "ctas_per_sm" (0 = occupancy maximum), "count_stats" / "profile" (0|1, see vpt_get_counters / vpt_get_kernel_times). */
 int  vpt_set_option(vpt_context* ctx, const char* key, int value);
 

@@ -193,7 +193,7 @@ k_generate(const FrameArgs fa)
             float3 p = madd3(org, dir, padd(t_min, VPT_EPS));
             int leaf = -2;
             if (!aabb_contains(sc.root_pmin, sc.root_pmax, p)) leaf = -1;
-            for (int it = 0; it < 256 && leaf == -2; ++it) leaf = oct_locate_or_skip(fs.oct, sc, p, dir);
+            for (int it = 0; it < 256 && leaf == -2; ++it) leaf = oct_locate_or_skip<true>(fs.oct, sc, p, dir);
             if (leaf == -1) {                                    // walked out through empty space: sample == miss sample
                 hit = false;
                 if (kp.integrator != 0) dir = normalize(dir);    // vol_integrator renormalises after a box hit (:1747)

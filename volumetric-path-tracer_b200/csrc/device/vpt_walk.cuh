@@ -133,8 +133,37 @@ VPT_DEV float oct_child_exit(const OctInternal& n, int c, float3 o, float3 d) {
 }
 
 // Returns leaf index 0..511, or -1 "outside the root box", or -2 "skipped an empty node" (ray_pos advanced).
+// kOneExit: one code site for the empty-child exit instead of one per level -- 64 instructions shorter; measured 2 % faster in k_generate
+// (2.23 -> 2.18 ms) and 0.5 % slower in the trace kernel's stepping loop, so each caller picks its form.  Same arithmetic either way.
+template <bool kOneExit = false>
 VPT_DEV int oct_locate_or_skip(const OctShared& oct, const SceneTables& sc, float3& ray_pos, float3 ray_dir) {
     if (!aabb_contains(sc.root_pmin, sc.root_pmax, ray_pos)) return -1;
+    if (kOneExit) {
+    // three levels of descent, ONE code site for the empty-child exit (the slab test of the child box is the bulky part)
+    const OctInternal* n = &oct.node[0];
+    int c = oct_child(*n, ray_pos);
+    int leaf = c * 64;
+    bool empty = (n->child_empty >> c) & 1u;
+    if (!empty) {
+        const int c1 = c;
+        n = &oct.node[1 + c1];
+        c = oct_child(*n, ray_pos);
+        leaf += c * 8;
+        empty = (n->child_empty >> c) & 1u;
+        if (!empty) {
+            n = &oct.node[9 + c1 * 8 + c];
+            c = oct_child(*n, ray_pos);
+            leaf += c;
+            empty = (n->child_empty >> c) & 1u;
+        }
+    }
+    if (empty) {
+        const float t_max = fmaxf(oct_child_exit(*n, c, ray_pos, ray_dir), 0.1f);
+        ray_pos = madd3(ray_pos, ray_dir, t_max);
+        return -2;
+    }
+    return leaf;
+    }
     const OctInternal& r = oct.node[0];
     const int c1 = oct_child(r, ray_pos);
     if ((r.child_empty >> c1) & 1u) {
