@@ -343,6 +343,8 @@ int vpt_render_passes(vpt_context* c, void* const params[VPT_NUM_ARGS], unsigned
         c->events.push_back(ev);
         return e;
     };
+    if (c->p2p_on && ((int)kp.resolution.x != c->p2p_w || (int)kp.resolution.y != c->p2p_h))
+        return fail(c, VPT_ERR_INVALID, "the peer exchange block was exported for another frame size (vpt_comm_p2p_export)");
     { int rc = vpt::comm_p2p_begin(c, stream); if (rc != VPT_OK) return rc; }      // multi-GPU peer exchange: this rank's frame may be overwritten from here on
     const uint32_t it0 = kp.iteration;
     const unsigned long long frame_px = (unsigned long long)kp.resolution.x * kp.resolution.y;
