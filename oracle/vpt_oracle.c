@@ -214,6 +214,9 @@ static v3 tex3d4(const float* d, const int dim[3], float u, float v, float w) {
     }
     return V((float)(acc[0] * (1.0 / 256.0)), (float)(acc[1] * (1.0 / 256.0)), (float)(acc[2] * (1.0 / 256.0)));
 }
+/* exported for tests/test_oracle_cpu.py: the 3-D filter alone, against vectors captured from the texture unit (tests/golden/tex_unit_*.npz) */
+float orc_tex3d(const float* data, int nx, int ny, int nz, float u, float v, float w) { const int dim[3] = { nx, ny, nz }; return tex3d1(data, dim, u, v, w); }
+
 static v3 tex2d_env(const orc_scene* s, float u, float v) {                          /* wrap in u, clamp in v (main.cpp:967-972) */
     float x = u * s->env_w - 0.5f, y = v * s->env_h - 0.5f;
     float fx = floorf(x), fy = floorf(y);
