@@ -48,7 +48,11 @@ int  vpt_abi_sizes(size_t* out, int n);
  * local frame has at most 2^20 pixels), "max_scratch_mb" (cap of the per-round ray queue + sample planes, default 12288),
  * "gather_async" (see vpt_comm_*),
  * "sched_min_lanes" (1..32, lanes an operation must gather in a warp before it pre-empts stepping, default 26),
- * "ctas_per_sm" (0 = occupancy maximum), "count_stats" / "profile" (0|1, see vpt_get_counters / vpt_get_kernel_times). */
+ * "trace_slots" (rays per lane of the trace kernel: 0 = by scene, the default -- 2 when the density grid is larger than twice the L2 or
+ * the scene has 64 or more instances, else 3; 2 or 3 to force it),
+ * "l2_sector_fetch" (0|1: while a cell table is set, ask the L2 for 32-byte DRAM fetches -- a device-wide hint, see vpt_set_cell_volume),
+ * "ctas_per_sm" (0 = occupancy maximum), "generic_kernel" (1: never pick the lean instantiation), "debug_flags" (development),
+ * "count_stats" / "profile" (0|1, see vpt_get_counters / vpt_get_kernel_times). */
 int  vpt_set_option(vpt_context* ctx, const char* key, int value);
 
 /* Multi-GPU partition of the frame: rank r of n renders the interleaved row stripes r, r+n, ... of
