@@ -47,7 +47,8 @@ int  vpt_abi_sizes(size_t* out, int n);
 /* Tunables: "passes_per_chunk" (1..64 passes fused per generate/trace/resolve round; 0 = automatic, the default: 32, or 64 when the
  * local frame has at most 2^20 pixels), "max_scratch_mb" (cap of the per-round ray queue + sample planes, default 12288),
  * "gather_async" (see vpt_comm_*),
- * "sched_min_lanes" (1..32, lanes an operation must gather in a warp before it pre-empts stepping, default 26),
+ * "sched_min_lanes" (1..32, lanes an operation must gather in a warp before it pre-empts stepping; 0 = by kernel, the default: 26 for the
+ * lean kernel at 3 rays per lane, else 20),
  * "trace_slots" (rays per lane of the trace kernel: 0 = by scene, the default -- 2 when the density grid is larger than twice the L2 or
  * the scene has 64 or more instances, else 3; 2 or 3 to force it),
  * "l2_sector_fetch" (0|1: while a cell table is set, ask the L2 for 32-byte DRAM fetches -- a device-wide hint, see vpt_set_cell_volume),

@@ -117,7 +117,7 @@ volume_rt_kernel(const vpt_camera cam, const vpt_light_list lights, const vpt_gp
         fa.cam = cam; fa.lights = lights; fa.kp = kernel_params; fa.sphere = &sphere; fa.scene = nullptr;
         fa.geom.width = W; fa.geom.height = H; fa.geom.local_rows = H; fa.geom.n_local = W * H; fa.geom.stripe_h = H > 0 ? H : 1; fa.geom.n_ranks = 1; fa.geom.rank = 0;
         fa.queue_dir = nullptr; fa.queue_id = nullptr; fa.queue_aux = nullptr; fa.thin_lens = cam.lens_radius != 0.0f ? 1 : 0;
-        fa.bn_table = nullptr; fa.n_passes = 1; fa.passes_per_block = 1; fa.tiles_per_block = 1; fa.debug_flags = 0; fa.sched_min_lanes = 26; fa.queue_count = nullptr; fa.queue_head = nullptr;
+        fa.bn_table = nullptr; fa.n_passes = 1; fa.passes_per_block = 1; fa.tiles_per_block = 1; fa.debug_flags = 0; fa.sched_min_lanes = 20; fa.queue_count = nullptr; fa.queue_head = nullptr;
         fa.planeA = fa.planeB = fa.planeC = nullptr;
         fa.planeD = reinterpret_cast<float4*>(kp.raw_buffer);          // env_pos scratch of the sphere branch: this pixel's raw_buffer entry, rewritten at the end
         fa.counters = nullptr; fa.cell_table = nullptr; fa.cell_nx = fa.cell_ny = fa.cell_nz = 0;

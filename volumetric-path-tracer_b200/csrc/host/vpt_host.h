@@ -40,7 +40,7 @@ struct vpt_context {
     size_t cap_samples = 0;           // n_local * chunk
     bool   cap_planeD = false;
     uint2* d_queue_id = nullptr; float4* d_queue_org = nullptr; float2* d_bn_table = nullptr; int cap_chunk = 0;
-    int sched_min_lanes = 26;
+    int sched_min_lanes = 0;          // option "sched_min_lanes": 0 = by kernel (26 for the lean kernel at 3 rays per lane, else 20)
     int debug_flags = 0;
     float4 *d_queue = nullptr, *d_planeA = nullptr, *d_planeB = nullptr, *d_planeC = nullptr, *d_planeD = nullptr;
     unsigned* d_counters = nullptr;   // [0] queue_count, [1] queue_head
